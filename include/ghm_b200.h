@@ -1,0 +1,165 @@
+/* ghm_b200.h -- C ABI of the B200-native JGHM sample + exact-BP library (libghm_b200.so).
+ *
+ * The reference (willcai7/Multimodal-GHM) has NO plugin / FFI interface for this
+ * path: the boundary is the Python module surface
+ *   src/ghmclip/data/data_random_GHM.py   (re-exported by src/ghmclip/data/__init__.py:5)
+ * Each entry point below names the reference function it replaces (file:line,
+ * relative to the reference root).  The Python facade in
+ * multimodal-ghm_b200/ghm_b200/ binds these with ctypes and mirrors the reference
+ * class/method surface on top of them.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a GHM_E* code otherwise;
+ *     ghm_last_error() returns a thread-local message for the last failure.
+ *   - device entry points take raw DEVICE pointers + sizes + a cudaStream_t passed
+ *     as void*; they never allocate or free caller memory and never synchronise.
+ *   - ghm_host_* entry points take HOST pointers, do their own H2D/D2H on the
+ *     model's internal stream and synchronise before returning.
+ *   - batch-major layouts: leaves [B, n_L]; posteriors [B, q]; z / mean [B, n_L];
+ *     next-token posteriors [B, n_L-1, q]; guides [B, n_L(-1), C]  (row-major).
+ *   - there is no CPU fallback anywhere: without a CUDA device every compute entry
+ *     point fails with GHM_ECUDA.
+ */
+#ifndef GHM_B200_H
+#define GHM_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GHM_API __attribute__((visibility("default")))
+#else
+#define GHM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GHM_OK        0
+#define GHM_EINVAL    1   /* bad argument (shape, dtype code, null pointer, unsupported q/L/s) */
+#define GHM_ECUDA     2   /* CUDA runtime error (message has the cudaError string) */
+#define GHM_ENOMEM    3
+#define GHM_EUNSUP    4   /* configuration outside what this build instantiates */
+
+/* leaf storage dtype codes */
+#define GHM_LEAF_I64  0   /* torch.long, the reference API dtype (data_random_GHM.py:697) */
+#define GHM_LEAF_U8   1   /* compact device format (q <= 256) */
+
+/* root modes for ghm_sample */
+#define GHM_ROOT_GIVEN    0   /* root_in supplied  (reference GHMTree(root=...), :153-156) */
+#define GHM_ROOT_PRIOR    1   /* draw from the model prior p_y (:158) */
+#define GHM_ROOT_UNIFORM  2   /* np.random.choice(q,size=B): uniform, ignores p_y (:674,758,858,906) */
+
+typedef struct ghm_model ghm_model_t;   /* opaque; owns only the device-side tables */
+
+GHM_API const char* ghm_last_error(void);
+GHM_API const char* ghm_version(void);
+/* number of CUDA devices visible, or -1 on a CUDA error */
+GHM_API int ghm_device_count(void);
+
+/* ---- model tables -------------------------------------------------------------
+ * Replaces the table side of SingleSampler/DoubleSampler.__init__ (:621-634,
+ * :645-658): the caller generates the transition matrices (GenTransition, :43-89)
+ * on the host and hands them over as float64.
+ *   T_host : [n_mat, q, q] row-major, T[m][a][b] = P(child=b | parent=a)
+ *            translation-invariant (ti=1): n_mat = L*s, m = (level-1)*s + child
+ *            per-edge (ti=0):              n_mat = E,   m = BFS edge index
+ *   p_y    : [q] root prior (NULL -> uniform)
+ * The library derives and uploads: f32 T, f32 T^T, f32 log T^T, f64 CDF (sequential
+ * cumsum, bit-identical to np.cumsum, :165) and u32 CDF thresholds (Philox mode). */
+GHM_API int ghm_model_create(ghm_model_t** out, int n_layer, int n_child, int q, int ti,
+                     const double* T_host, const double* p_y_host, int device);
+GHM_API int ghm_model_destroy(ghm_model_t* m);
+GHM_API int ghm_model_info(const ghm_model_t* m, int* n_layer, int* n_child, int* q, int* ti,
+                   int64_t* n_leaves, int64_t* n_edges);
+/* sticky device-side status word (bit0: a leaf/root value >= q was clamped).
+ * Synchronises `stream`; for tests / debugging only. */
+GHM_API int ghm_model_status(ghm_model_t* m, void* stream, int* status_out);
+
+/* ---- K1: sampler  (GHMTree.gen_values, :145-165) -------------------------------
+ *   U        : f64 [E, B] uniforms in BFS-edge-major order = the reference's E
+ *              sequential np.random.rand(B,1) calls -> PARITY mode, f64 compare,
+ *              leaves bit-identical to the reference.  NULL -> Philox4x32-10 keyed by
+ *              (seed; global tree index = tree_offset + b, level, node).
+ *   root_in  : i64 [B] when root_mode == GHM_ROOT_GIVEN, else ignored
+ *   root_out : i64 [B] or NULL;  leaves_out : [B, n_L] of leaf_dtype or NULL
+ *   post_out / root_hd_out : f32 [B, q] or NULL -> when given, BP_CLS (:185-221) is
+ *              fused into the same pass (leaf states never leave the SM). */
+GHM_API int ghm_sample(const ghm_model_t* m, int64_t B, int root_mode, const int64_t* root_in,
+               const double* U, uint64_t seed, uint64_t tree_offset,
+               int64_t* root_out, void* leaves_out, int leaf_dtype,
+               float* post_out, float* root_hd_out, void* stream);
+
+/* ---- K2: root posterior  (GHMTree.BP_CLS, :185-221) ----------------------------
+ *   post     : f32 [B, q]  p(root | leaves)               (posterior_probability_CLS^T)
+ *   root_hd  : f32 [B, q]  max-shifted log-likelihood, NO prior (root_node.hd_message^T,
+ *              the cross-modal "external" message, :871,919)   (either may be NULL) */
+GHM_API int ghm_bp_cls(const ghm_model_t* m, int64_t B, const void* leaves, int leaf_dtype,
+               float* post, float* root_hd, void* stream);
+
+/* ---- K3: Gaussian denoiser  (GHMTree.BP_DNS, :467-523) -------------------------
+ *   z : f32 [B, n_L]; ext : f32 [B, q] external root log-message or NULL;
+ *   mean : f32 [B, n_L] posterior mean of every leaf (posterior_mean_DNS^T)
+ *   workspace : device scratch of ghm_bp_dns_workspace_bytes(m, B) bytes */
+GHM_API int64_t ghm_bp_dns_workspace_bytes(const ghm_model_t* m, int64_t B);
+GHM_API int ghm_bp_dns(const ghm_model_t* m, int64_t B, const float* z, float sigma, const float* ext,
+               float* mean, void* workspace, void* stream);
+
+/* ---- K4: next-token posterior  (GHMTree.BP_NWP_autoregressive, :336-463) -------
+ *   pp : f32 [B, n_L-1, q],  pp[b,t,:] = p(leaf_{t+1} | leaves_{<=t}, ext) */
+GHM_API int64_t ghm_bp_nwp_workspace_bytes(const ghm_model_t* m, int64_t B);
+GHM_API int ghm_bp_nwp(const ghm_model_t* m, int64_t B, const void* leaves, int leaf_dtype,
+               const float* ext, float* pp, void* workspace, void* stream);
+
+/* ---- K5: guide tensors  (GHMTree.guided_info, :526-592; NWP guides :357-459) ---
+ * Log-domain BP with the reference's exact shift conventions, written straight in
+ * the [B, n_L, C] f32 layout the guided losses index.  `guides` is an array of
+ * DEVICE pointers living in HOST memory (read at enqueue time).
+ *   cls : L tensors [B,n_L,q]           (depth L-1 .. 0 hd)
+ *   dns : 2L+1 tensors [B,n_L,2q] x L, [B,n_L,2q], [B,n_L,3q] x L
+ *   nwp : 2L+1 tensors [B,n_L-1,{q,2q..,2q,q..}]                                  */
+GHM_API int ghm_guides_cls(const ghm_model_t* m, int64_t B, const void* leaves, int leaf_dtype,
+                   float* const* guides, float* post, float* root_hd, void* stream);
+GHM_API int64_t ghm_guides_dns_workspace_bytes(const ghm_model_t* m, int64_t B);
+GHM_API int ghm_guides_dns(const ghm_model_t* m, int64_t B, const float* z, float sigma, const float* ext,
+                   float* const* guides, float* mean, void* workspace, void* stream);
+GHM_API int64_t ghm_guides_nwp_workspace_bytes(const ghm_model_t* m, int64_t B);
+GHM_API int ghm_guides_nwp(const ghm_model_t* m, int64_t B, const void* leaves, int leaf_dtype,
+                   const float* ext, float* const* guides, float* pp, void* workspace, void* stream);
+
+/* ---- K6: risk reductions --------------------------------------------------------
+ * Every risk kernel ACCUMULATES (atomically, f64) into sums[3] = {sum, sum of squares,
+ * count}; the caller zeroes it, and may all-reduce it across ranks before mean / SE.
+ *   clip : PPCLIPLoss == ClipSampler.get_Bayes == clip_loss_compute (:13-41,:794-817,
+ *          :819-844).  t_pp, i_pp : f32 [n*(K+1), q] in the ClipSampler block layout
+ *          (:758-760).  Pairs [pair_lo, pair_hi) only (multi-GPU: shard on the pair).
+ *   cdm  : ConditionalDenoiseSampler.get_Bayes (:886-894): per tree sum_leaf (mean-x)^2
+ *   ce   : token / root cross-entropy -log p[b, target[b]]  (NextWordPredictSampler.get_Bayes
+ *          :931-942 with rows = B*(n_L-1); ClassificationSampler.get_Bayes :707-720)     */
+GHM_API int ghm_risk_clip(const float* t_pp, const float* i_pp, int64_t n, int K, int q,
+                  int64_t pair_lo, int64_t pair_hi, double* sums, void* stream);
+GHM_API int ghm_risk_cdm(const float* mean, const void* leaves, int leaf_dtype, int64_t B, int64_t n_leaves,
+                 double* sums, void* stream);
+GHM_API int ghm_risk_ce(const float* pp, const void* target, int leaf_dtype, int64_t rows, int q,
+                int64_t target_stride, int64_t target_offset, int64_t row_group,
+                double* sums, void* stream);
+
+/* ---- Gaussian observations  (image_tree_noise, :733,:867) -----------------------
+ * z[b,i] = leaves[b,i] + sigma * N(0,1), Philox stream 1 keyed like ghm_sample. */
+GHM_API int ghm_gauss_noise(const ghm_model_t* m, int64_t B, const void* leaves, int leaf_dtype, float sigma,
+                    uint64_t seed, uint64_t tree_offset, float* z, void* stream);
+
+/* ---- host-buffer entry points (end-to-end measurement / non-torch callers) ------
+ * ClipSampler.get_Bayes (:786-817) in one call: host roots are NOT needed (roots are
+ * drawn on the device, uniform as in :758-759).  sums_host[3] receives the reduced
+ * {sum, sum sq, count}.  Optional host outputs (may be NULL): leaves as leaf_dtype
+ * [n*(K+1), n_L] and posteriors f32 [n*(K+1), q] for each modality. */
+GHM_API int ghm_host_clip_bayes(const ghm_model_t* text, const ghm_model_t* image, int64_t n, int K,
+                        uint64_t seed, uint64_t tree_offset, double* sums_host,
+                        void* t_leaves_host, void* i_leaves_host, int leaf_dtype,
+                        float* t_pp_host, float* i_pp_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GHM_B200_H */

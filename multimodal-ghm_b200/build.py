@@ -1,0 +1,71 @@
+"""Build libghm_b200.so in-tree with nvcc for sm_100a (no torch headers, plain C ABI).
+
+    python multimodal-ghm_b200/build.py [--force] [--verbose]
+
+Each csrc/*.cu is compiled to an object in parallel, then linked into
+multimodal-ghm_b200/ghm_b200/libghm_b200.so (git-ignored; it travels to the GPU box).
+"""
+import concurrent.futures as cf
+import glob
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "ghm_b200")
+BUILD = os.path.join(HERE, "build")
+LIB = os.path.join(OUT_DIR, "libghm_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+
+
+def _deps_hash(src):
+    h = hashlib.sha1()
+    for f in [src] + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
+            sorted(glob.glob(os.path.join(HERE, "..", "include", "*.h"))):
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile(src, force, verbose):
+    obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
+    stamp = obj + ".sha1"
+    hh = _deps_hash(src)
+    if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == hh:
+        return obj, False, ""
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    with open(stamp, "w") as f:
+        f.write(hh)
+    return obj, True, r.stderr
+
+
+def build(force=False, verbose=False):
+    os.makedirs(BUILD, exist_ok=True)
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    if not srcs:
+        raise RuntimeError("no CUDA sources under " + CSRC)
+    with cf.ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
+        res = list(ex.map(lambda s: _compile(s, force, verbose), srcs))
+    objs = [r[0] for r in res]
+    if verbose:
+        for r in res:
+            if r[2]:
+                sys.stderr.write(r[2])
+    if any(r[1] for r in res) or not os.path.exists(LIB):
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

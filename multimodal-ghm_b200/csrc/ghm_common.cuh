@@ -1,0 +1,128 @@
+// ghm_common.cuh -- shared device/host definitions for libghm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/ghm_b200.h"
+
+#define GHM_MAX_LEVELS 16          // L <= 16
+#define GHM_MAX_Q_REG  16          // register-resident kernels: q <= 16 (padded to Q in {4,8,10,16})
+
+// ------------------------------------------------------------------------------------
+// Device-visible model descriptor, passed BY VALUE as a kernel parameter.
+//
+// Tables (one entry per matrix m; translation-invariant models have L*s matrices, per-edge
+// models have E).  All rows/columns are padded with zeros from q up to QP = padded q:
+//   Tlin  [m][a][b]   f32  P(child=b | parent=a)              (up / down matvecs)
+//   TlinT [m][b][a]   f32  same, transposed                   (leaf column gather, linear)
+//   TlogT [m][b][a]   f32  natural log of the above           (leaf column gather, log domain)
+//   cdfu  [m][a][k]   u32  floor(cumsum_k T[a][:] * 2^32), padded with 0xFFFFFFFF   (Philox mode)
+//   cdfd  [m][a][k]   f64  sequential cumsum, unpadded stride q                     (parity mode)
+// ------------------------------------------------------------------------------------
+struct GhmDev {
+    int L, s, q, QP, ti;
+    int n_mat;
+    int n_leaves;                          // s^L
+    int n_edges;                           // sum_{l=1..L} s^l
+    int mat_off[GHM_MAX_LEVELS + 1];       // mat_off[l]: first matrix of edges INTO depth l (l=1..L)
+    int edge_off[GHM_MAX_LEVELS + 1];      // edge_off[l]: BFS edge index of node 0 at depth l (l=1..L)
+    int spow[GHM_MAX_LEVELS + 1];          // s^l
+    unsigned s_magic;                      // ceil(2^32 / s): idx / s == __umulhi(idx, s_magic) for idx < 2^28
+    unsigned pow_magic[GHM_MAX_LEVELS + 1]; // ceil(2^32 / s^k), k>=1: j / s^k == __umulhi(j, .) for j*s^k < 2^32
+    const float* Tlin;
+    const float* TlinT;
+    const float* TlogT;
+    const uint32_t* cdfu;
+    const double* cdfd;
+    const float* py;                       // [QP] prior, zero padded
+    const uint32_t* root_cdfu_prior;       // [QP]
+    const uint32_t* root_cdfu_unif;        // [QP]
+    int* status;                           // sticky device status word
+};
+
+struct ghm_model {
+    GhmDev d;
+    int device;
+    void* slab;          // single device allocation holding every table
+    size_t slab_bytes;
+    cudaStream_t stream; // internal stream for ghm_host_* entry points
+    // host scratch for ghm_host_* (lazily sized)
+    void* h_scratch; size_t h_scratch_bytes;
+    void* d_scratch; size_t d_scratch_bytes;
+};
+
+// ------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------
+void ghm_set_error(const std::string& msg);
+int ghm_fail(int code, const char* fmt, ...);
+
+#define GHM_CUDA_TRY(expr)                                                                 \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return ghm_fail(GHM_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                           \
+    } while (0)
+
+#define GHM_CHECK_LAUNCH()                                                                 \
+    do {                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess)                                                             \
+            return ghm_fail(GHM_ECUDA, "kernel launch failed: %s (%s:%d)",                 \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                   \
+    } while (0)
+
+// padded q used by the register-resident kernels; 0 when q is outside their range
+static inline int ghm_pad_q(int q) {
+    if (q <= 4) return 4;
+    if (q <= 8) return 8;
+    if (q <= 10) return 10;
+    if (q <= 16) return 16;
+    return 0;
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter = (tree_lo, tree_hi, block, level|stream<<8),
+// key = (seed_lo, seed_hi).  One call yields 4 x 32 random bits; word (node & 3) of block
+// (node >> 2) of level l is the draw for BFS node `node` at depth l.  Restated in numpy by
+// oracle/philox.py so Philox-mode samples are checkable bit-for-bit.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0;
+        k.y += W1;
+    }
+    return c;
+}
+
+#define GHM_STREAM_TREE  0u
+#define GHM_STREAM_NOISE 1u
+
+__device__ __forceinline__ uint4 ghm_rng_block(uint64_t seed, uint64_t tree, uint32_t level, uint32_t block,
+                                               uint32_t stream) {
+    return philox4x32_10(make_uint4((uint32_t)tree, (uint32_t)(tree >> 32), block, level | (stream << 8)),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+__device__ __forceinline__ uint32_t ghm_pick(const uint4& v, int w) {
+    return w == 0 ? v.x : (w == 1 ? v.y : (w == 2 ? v.z : v.w));
+}
+
+// idx / s for uniform small integers
+__device__ __forceinline__ int ghm_div_s(int idx, const GhmDev& d) {
+    return d.s == 1 ? idx : (int)__umulhi((unsigned)idx, d.s_magic);
+}
+// j / s^k (k >= 0)
+__device__ __forceinline__ int ghm_div_pow(int j, int k, const GhmDev& d) {
+    return (k == 0 || d.s == 1) ? j : (int)__umulhi((unsigned)j, d.pow_magic[k]);
+}
+#endif  // __CUDACC__

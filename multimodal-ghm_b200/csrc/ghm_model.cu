@@ -1,0 +1,205 @@
+// ghm_model.cu -- model tables, error plumbing, misc C-ABI entry points.
+//
+// Replaces the table side of the reference's SingleSampler/DoubleSampler constructors
+// (src/ghmclip/data/data_random_GHM.py:621-634, :645-658): the host generates the
+// transition matrices (GenTransition, :43-89) and this file derives every device table.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "ghm_common.cuh"
+
+static thread_local std::string g_last_error;
+
+void ghm_set_error(const std::string& msg) { g_last_error = msg; }
+
+int ghm_fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+extern "C" const char* ghm_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* ghm_version(void) { return "ghm_b200 0.1 (sm_100a)"; }
+
+extern "C" int ghm_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        ghm_fail(GHM_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return -1;
+    }
+    return n;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, const double* T_host,
+                                const double* p_y_host, int device) {
+    if (!out || !T_host) return ghm_fail(GHM_EINVAL, "ghm_model_create: null argument");
+    if (L < 1 || L > GHM_MAX_LEVELS) return ghm_fail(GHM_EINVAL, "n_layer=%d outside [1,%d]", L, GHM_MAX_LEVELS);
+    if (s < 1 || s > 64) return ghm_fail(GHM_EINVAL, "n_child=%d outside [1,64]", s);
+    if (q < 2 || q > 256) return ghm_fail(GHM_EINVAL, "variable_type=%d outside [2,256]", q);
+    double nl = pow((double)s, (double)L);
+    if (nl > 65536.0) return ghm_fail(GHM_EINVAL, "s^L = %.0f leaves is too large (max 65536)", nl);
+
+    ghm_model* m = new ghm_model();
+    memset(m, 0, sizeof *m);
+    GhmDev& d = m->d;
+    d.L = L; d.s = s; d.q = q; d.ti = ti ? 1 : 0;
+    d.QP = ghm_pad_q(q) ? ghm_pad_q(q) : (int)align_up(q, 4);
+    const int QP = d.QP;
+    d.spow[0] = 1;
+    for (int l = 1; l <= L; ++l) d.spow[l] = d.spow[l - 1] * s;
+    for (int l = L + 1; l <= GHM_MAX_LEVELS; ++l) d.spow[l] = 0;
+    d.n_leaves = d.spow[L];
+    int e = 0;
+    for (int l = 1; l <= L; ++l) {
+        d.edge_off[l] = e;
+        d.mat_off[l] = d.ti ? (l - 1) * s : e;
+        e += d.spow[l];
+    }
+    d.n_edges = e;
+    d.n_mat = d.ti ? L * s : e;
+    d.s_magic = s >= 2 ? (unsigned)((0x100000000ull + (unsigned)s - 1) / (unsigned)s) : 0u;
+    for (int k = 0; k <= GHM_MAX_LEVELS; ++k)
+        d.pow_magic[k] = (k >= 1 && k <= L && d.spow[k] >= 2)
+                             ? (unsigned)((0x100000000ull + (unsigned)d.spow[k] - 1) / (unsigned)d.spow[k]) : 0u;
+    m->device = device;
+
+    // ---- derive the host tables ---------------------------------------------------
+    const size_t nm = (size_t)d.n_mat, QQ = (size_t)QP * QP;
+    std::vector<float> Tlin(nm * QQ, 0.f), TlinT(nm * QQ, 0.f), TlogT(nm * QQ, -INFINITY);
+    std::vector<uint32_t> cdfu(nm * QQ, 0xFFFFFFFFu);
+    std::vector<double> cdfd(nm * (size_t)q * q, 0.0);
+    for (size_t mi = 0; mi < nm; ++mi) {
+        const double* T = T_host + mi * (size_t)q * q;
+        for (int a = 0; a < q; ++a) {
+            double run = 0.0;
+            for (int b = 0; b < q; ++b) {
+                double t = T[(size_t)a * q + b];
+                if (!(t >= 0.0) || !isfinite(t)) {
+                    delete m;
+                    return ghm_fail(GHM_EINVAL, "transition[%zu][%d][%d]=%g is not a probability", mi, a, b, t);
+                }
+                Tlin[mi * QQ + (size_t)a * QP + b] = (float)t;
+                TlinT[mi * QQ + (size_t)b * QP + a] = (float)t;
+                TlogT[mi * QQ + (size_t)b * QP + a] = (float)log(t);
+                run = (b == 0) ? t : run + t;                 // np.cumsum: sequential f64 adds
+                cdfd[mi * (size_t)q * q + (size_t)a * q + b] = run;
+                double thr = floor(run * 4294967296.0);
+                cdfu[mi * QQ + (size_t)a * QP + b] = thr >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr;
+            }
+        }
+    }
+    std::vector<float> py(QP, 0.f);
+    std::vector<uint32_t> rc_prior(QP, 0xFFFFFFFFu), rc_unif(QP, 0xFFFFFFFFu);
+    {
+        double run = 0.0, runu = 0.0;
+        for (int a = 0; a < q; ++a) {
+            double p = p_y_host ? p_y_host[a] : 1.0 / q;
+            if (!(p >= 0.0)) { delete m; return ghm_fail(GHM_EINVAL, "p_y[%d]=%g is not a probability", a, p); }
+            py[a] = (float)p;
+            run += p; runu += 1.0 / q;
+            double t1 = floor(run * 4294967296.0), t2 = floor(runu * 4294967296.0);
+            rc_prior[a] = t1 >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t1;
+            rc_unif[a] = t2 >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t2;
+        }
+    }
+
+    // ---- one device slab ----------------------------------------------------------
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_Tlin = take(Tlin.size() * 4), o_TlinT = take(TlinT.size() * 4), o_TlogT = take(TlogT.size() * 4);
+    size_t o_cdfu = take(cdfu.size() * 4), o_cdfd = take(cdfd.size() * 8);
+    size_t o_py = take(py.size() * 4), o_rcp = take(rc_prior.size() * 4), o_rcu = take(rc_unif.size() * 4);
+    size_t o_status = take(sizeof(int));
+    m->slab_bytes = off;
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        delete m;
+        return ghm_fail(GHM_ECUDA, "no CUDA device available (%s): libghm_b200 has no CPU fallback",
+                        ce == cudaSuccess ? "0 devices" : cudaGetErrorString(ce));
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+#define MC_TRY(expr)                                                                         \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            if (m->slab) cudaFree(m->slab);                                                  \
+            cudaSetDevice(prev);                                                             \
+            delete m;                                                                        \
+            return ghm_fail(GHM_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));      \
+        }                                                                                    \
+    } while (0)
+    MC_TRY(cudaSetDevice(device));
+    MC_TRY(cudaMalloc(&m->slab, m->slab_bytes));
+    char* base = (char*)m->slab;
+    MC_TRY(cudaMemcpy(base + o_Tlin, Tlin.data(), Tlin.size() * 4, cudaMemcpyHostToDevice));
+    MC_TRY(cudaMemcpy(base + o_TlinT, TlinT.data(), TlinT.size() * 4, cudaMemcpyHostToDevice));
+    MC_TRY(cudaMemcpy(base + o_TlogT, TlogT.data(), TlogT.size() * 4, cudaMemcpyHostToDevice));
+    MC_TRY(cudaMemcpy(base + o_cdfu, cdfu.data(), cdfu.size() * 4, cudaMemcpyHostToDevice));
+    MC_TRY(cudaMemcpy(base + o_cdfd, cdfd.data(), cdfd.size() * 8, cudaMemcpyHostToDevice));
+    MC_TRY(cudaMemcpy(base + o_py, py.data(), py.size() * 4, cudaMemcpyHostToDevice));
+    MC_TRY(cudaMemcpy(base + o_rcp, rc_prior.data(), rc_prior.size() * 4, cudaMemcpyHostToDevice));
+    MC_TRY(cudaMemcpy(base + o_rcu, rc_unif.data(), rc_unif.size() * 4, cudaMemcpyHostToDevice));
+    MC_TRY(cudaMemset(base + o_status, 0, sizeof(int)));
+    MC_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    MC_TRY(cudaSetDevice(prev));
+#undef MC_TRY
+    d.Tlin = (const float*)(base + o_Tlin);
+    d.TlinT = (const float*)(base + o_TlinT);
+    d.TlogT = (const float*)(base + o_TlogT);
+    d.cdfu = (const uint32_t*)(base + o_cdfu);
+    d.cdfd = (const double*)(base + o_cdfd);
+    d.py = (const float*)(base + o_py);
+    d.root_cdfu_prior = (const uint32_t*)(base + o_rcp);
+    d.root_cdfu_unif = (const uint32_t*)(base + o_rcu);
+    d.status = (int*)(base + o_status);
+    *out = m;
+    return GHM_OK;
+}
+
+extern "C" int ghm_model_destroy(ghm_model_t* m) {
+    if (!m) return GHM_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->slab) cudaFree(m->slab);
+    if (m->d_scratch) cudaFree(m->d_scratch);
+    if (m->h_scratch) cudaFreeHost(m->h_scratch);
+    cudaSetDevice(prev);
+    delete m;
+    return GHM_OK;
+}
+
+extern "C" int ghm_model_info(const ghm_model_t* m, int* L, int* s, int* q, int* ti, int64_t* n_leaves,
+                              int64_t* n_edges) {
+    if (!m) return ghm_fail(GHM_EINVAL, "ghm_model_info: null model");
+    if (L) *L = m->d.L;
+    if (s) *s = m->d.s;
+    if (q) *q = m->d.q;
+    if (ti) *ti = m->d.ti;
+    if (n_leaves) *n_leaves = m->d.n_leaves;
+    if (n_edges) *n_edges = m->d.n_edges;
+    return GHM_OK;
+}
+
+extern "C" int ghm_model_status(ghm_model_t* m, void* stream, int* status_out) {
+    if (!m || !status_out) return ghm_fail(GHM_EINVAL, "ghm_model_status: null argument");
+    GHM_CUDA_TRY(cudaMemcpyAsync(status_out, m->d.status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    GHM_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return GHM_OK;
+}

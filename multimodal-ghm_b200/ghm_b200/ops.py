@@ -1,0 +1,217 @@
+"""Torch-tensor wrappers over libghm_b200's C ABI (device pointers + current CUDA stream).
+
+Every function allocates its outputs with ``torch.empty`` on the model's device, passes raw
+``data_ptr()``s and ``torch.cuda.current_stream().cuda_stream`` and returns torch tensors.
+Nothing here computes on the CPU: without the CUDA library or a GPU these raise.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import check, get_lib
+
+LEAF_I64, LEAF_U8 = 0, 1
+ROOT_GIVEN, ROOT_PRIOR, ROOT_UNIFORM = 0, 1, 2
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _leaf_code(t):
+    if t.dtype == torch.int64:
+        return LEAF_I64
+    if t.dtype == torch.uint8:
+        return LEAF_U8
+    raise TypeError("leaves must be int64 or uint8, got %s" % t.dtype)
+
+
+def is_translation_invariant(transition, n_child):
+    """True when every level tiles the same n_child matrices (reference GenTransition TI mode, :71-76)."""
+    for level in transition:
+        for i, m in enumerate(level):
+            ref = level[i % n_child]
+            if m is not ref and not np.array_equal(m, ref):
+                return False
+    return True
+
+
+class GhmModel:
+    """Device-side tables of one tree family (transition matrices + prior).  Immutable after creation.
+
+    ``transition`` is the reference's structure: list[L] of list[s**(l+1)] of (q,q) float64
+    (``GenTransition`` output / ``sampler.transition``).
+    """
+
+    def __init__(self, transition, n_layer, n_child, variable_type, p_y=None, device=None):
+        lib = get_lib()
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        self.device = torch.device("cuda", dev.index if dev.index is not None else 0)
+        self.L, self.s, self.q = int(n_layer), int(n_child), int(variable_type)
+        assert len(transition) == self.L
+        self.ti = is_translation_invariant(transition, self.s)
+        mats = []
+        for l, level in enumerate(transition):
+            assert len(level) == self.s ** (l + 1), "level %d has %d matrices" % (l, len(level))
+            mats.extend(level[:self.s] if self.ti else level)
+        T = np.ascontiguousarray(np.stack([np.asarray(m, dtype=np.float64) for m in mats]))
+        assert T.shape[1:] == (self.q, self.q)
+        py = None if p_y is None else np.ascontiguousarray(np.asarray(p_y, dtype=np.float64))
+        self.n_leaves = self.s ** self.L
+        self.n_edges = sum(self.s ** l for l in range(1, self.L + 1))
+        h = C.c_void_p()
+        check(lib.ghm_model_create(C.byref(h), self.L, self.s, self.q, int(self.ti), T.ctypes.data_as(C.c_void_p),
+                                   py.ctypes.data_as(C.c_void_p) if py is not None else C.c_void_p(0),
+                                   self.device.index))
+        self._h = h
+        self._lib = lib
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.ghm_model_destroy(h)
+            except Exception:
+                pass
+
+    def status(self):
+        out = C.c_int(0)
+        with torch.cuda.device(self.device):
+            check(self._lib.ghm_model_status(self._h, _stream(), C.byref(out)))
+        return out.value
+
+    # ---- K1 (+ optional fused K2) ------------------------------------------------------
+    def sample(self, batch, root=None, U=None, seed=0, tree_offset=0, root_mode=None, leaf_dtype=torch.int64,
+               want_leaves=True, want_root=True, want_post=False, want_root_hd=False):
+        """Sample ``batch`` trees.  Returns dict(root, leaves, post, root_hd) (absent -> None).
+
+        ``U`` (float64 [E,B], device) selects parity mode (reference uniforms, bit-exact leaves);
+        otherwise Philox keyed by (seed, tree_offset + b).
+        """
+        B = int(batch)
+        dev = self.device
+        with torch.cuda.device(dev):
+            if root is not None:
+                root = torch.as_tensor(root).to(device=dev, dtype=torch.int64).contiguous()
+                assert root.numel() == B
+                mode = ROOT_GIVEN
+            else:
+                mode = ROOT_PRIOR if root_mode is None else root_mode
+            if U is not None:
+                U = torch.as_tensor(U).to(device=dev, dtype=torch.float64).contiguous()
+                assert tuple(U.shape) == (self.n_edges, B), "U must be [E=%d, B=%d]" % (self.n_edges, B)
+            root_out = torch.empty(B, dtype=torch.int64, device=dev) if want_root else None
+            leaves = torch.empty((B, self.n_leaves), dtype=leaf_dtype, device=dev) if want_leaves else None
+            post = torch.empty((B, self.q), dtype=torch.float32, device=dev) if want_post else None
+            hd = torch.empty((B, self.q), dtype=torch.float32, device=dev) if want_root_hd else None
+            check(self._lib.ghm_sample(self._h, B, mode, _ptr(root), _ptr(U), seed, tree_offset, _ptr(root_out),
+                                       _ptr(leaves), _leaf_code(leaves) if leaves is not None else LEAF_I64,
+                                       _ptr(post), _ptr(hd), _stream()))
+        return {"root": root_out, "leaves": leaves, "post": post, "root_hd": hd}
+
+    # ---- K2 ---------------------------------------------------------------------------
+    def bp_cls(self, leaves):
+        """leaves [B, n_L] (int64/uint8, device) -> (post [B,q] f32, root_hd [B,q] f32)."""
+        leaves = leaves.contiguous()
+        B = leaves.shape[0]
+        assert leaves.shape[1] == self.n_leaves and leaves.device == self.device
+        with torch.cuda.device(self.device):
+            post = torch.empty((B, self.q), dtype=torch.float32, device=self.device)
+            hd = torch.empty((B, self.q), dtype=torch.float32, device=self.device)
+            check(self._lib.ghm_bp_cls(self._h, B, _ptr(leaves), _leaf_code(leaves), _ptr(post), _ptr(hd), _stream()))
+        return post, hd
+
+    # ---- Gaussian observations ---------------------------------------------------------
+    def gauss_noise(self, leaves, sigma, seed=0, tree_offset=0):
+        """z = leaves + sigma*N(0,1) (Philox stream 1) -> f32 [B, n_L]."""
+        leaves = leaves.contiguous()
+        B = leaves.shape[0]
+        with torch.cuda.device(self.device):
+            z = torch.empty((B, self.n_leaves), dtype=torch.float32, device=self.device)
+            check(self._lib.ghm_gauss_noise(self._h, B, _ptr(leaves), _leaf_code(leaves), float(sigma), seed,
+                                            tree_offset, _ptr(z), _stream()))
+        return z
+
+
+IMAGE_SEED_XOR = 0x1234567887654321
+
+
+def new_sums(device):
+    """Zeroed {sum, sum of squares, count} accumulator (float64[3]) for the risk kernels."""
+    return torch.zeros(3, dtype=torch.float64, device=device)
+
+
+def risk_clip(t_pp, i_pp, n, K, q, sums=None, pair_lo=0, pair_hi=None):
+    """Accumulate the symmetric K-way Bayes CLIP loss of pairs [pair_lo, pair_hi) into ``sums``."""
+    lib = get_lib()
+    t_pp, i_pp = t_pp.contiguous(), i_pp.contiguous()
+    assert t_pp.dtype == torch.float32 and i_pp.dtype == torch.float32
+    assert tuple(t_pp.shape) == (n * (K + 1), q) and tuple(i_pp.shape) == (n * (K + 1), q)
+    pair_hi = n if pair_hi is None else pair_hi
+    with torch.cuda.device(t_pp.device):
+        if sums is None:
+            sums = new_sums(t_pp.device)
+        check(lib.ghm_risk_clip(_ptr(t_pp), _ptr(i_pp), n, K, q, pair_lo, pair_hi, _ptr(sums), _stream()))
+    return sums
+
+
+def risk_cdm(mean, leaves, sums=None):
+    """Accumulate per-tree sum_leaf (mean - x)^2 into ``sums``."""
+    lib = get_lib()
+    mean, leaves = mean.contiguous(), leaves.contiguous()
+    assert mean.dtype == torch.float32 and mean.shape == leaves.shape
+    with torch.cuda.device(mean.device):
+        if sums is None:
+            sums = new_sums(mean.device)
+        check(lib.ghm_risk_cdm(_ptr(mean), _ptr(leaves), _leaf_code(leaves), mean.shape[0], mean.shape[1],
+                               _ptr(sums), _stream()))
+    return sums
+
+
+def risk_ce(pp, target, sums=None, target_stride=1, target_offset=0, row_group=1):
+    """Accumulate -log pp[r, target(r)] over rows; target(r) = target[(r//g)*stride + offset + r%g]."""
+    lib = get_lib()
+    pp, target = pp.contiguous(), target.contiguous()
+    q = pp.shape[-1]
+    rows = pp.numel() // q
+    with torch.cuda.device(pp.device):
+        if sums is None:
+            sums = new_sums(pp.device)
+        check(lib.ghm_risk_ce(_ptr(pp), _ptr(target), _leaf_code(target), rows, q, target_stride, target_offset,
+                              row_group, _ptr(sums), _stream()))
+    return sums
+
+
+def mean_se(sums, se_count=None):
+    """(mean, std/sqrt(se_count)) from {sum, sumsq, count}; population std like np.std (reference :41,817,894)."""
+    s1, s2, c = (float(x) for x in sums.tolist())
+    mean = s1 / c
+    var = max(s2 / c - mean * mean, 0.0)
+    return mean, (var ** 0.5) / ((se_count if se_count else c) ** 0.5)
+
+
+def host_clip_bayes(text, image, n, K=4, seed=0, tree_offset=0, leaves_out=None, pp_out=None):
+    """ClipSampler.get_Bayes through the HOST-buffer C entry point (its own stream, H2D/D2H inside).
+
+    ``leaves_out`` = (t_leaves, i_leaves) and ``pp_out`` = (t_pp, i_pp): optional pre-allocated
+    (ideally pinned) CPU tensors to receive what ClipSampler.get_batch returns.
+    """
+    lib = get_lib()
+    sums = np.zeros(3, dtype=np.float64)
+    tl = il = tp = ip = None
+    code = LEAF_I64
+    if leaves_out is not None:
+        tl, il = leaves_out
+        code = _leaf_code(tl)
+    if pp_out is not None:
+        tp, ip = pp_out
+    check(lib.ghm_host_clip_bayes(text._h, image._h, n, K, seed, tree_offset, sums.ctypes.data_as(C.c_void_p),
+                                  _ptr(tl), _ptr(il), code, _ptr(tp), _ptr(ip)))
+    return sums

@@ -1,0 +1,169 @@
+"""GPU parity tests for K1 (sampler), K2 (root-posterior BP) and K6 (CLIP risk) through the C ABI.
+
+Oracle = oracle/ghm_oracle.py (pinned to the reference by tests/test_oracle_golden.py) plus
+the committed reference fixtures in tests/golden/.  Bars: integers bit-exact; BP marginals
+within 1e-5 relative (float32), as BASELINE.json's north_star states.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TREE_CASES, load_tree_case
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ghm_b200 import ops as _ops
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return _ops
+
+
+def _model(ops, c):
+    return ops.GhmModel(c["T"], c["L"], c["s"], c["q"], p_y=c["p_y"], device="cuda:0")
+
+
+@pytest.mark.parametrize("name", TREE_CASES)
+def test_parity_sampling_bit_exact_vs_reference_fixture(ops, name):
+    """Same root + same uniforms as the reference -> identical leaves (reference :145-165)."""
+    c = load_tree_case(name)
+    m = _model(ops, c)
+    for dt in (torch.int64, torch.uint8):
+        out = m.sample(c["B"], root=c["root"], U=torch.from_numpy(c["U"]).cuda(), leaf_dtype=dt)
+        assert np.array_equal(out["leaves"].cpu().numpy().astype(np.int64), c[f"val{c['L']}"].T)
+        assert np.array_equal(out["root"].cpu().numpy(), c["root"])
+    assert m.status() == 0
+
+
+@pytest.mark.parametrize("name", TREE_CASES)
+def test_bp_cls_vs_reference_fixture(ops, name):
+    c = load_tree_case(name)
+    m = _model(ops, c)
+    leaves = torch.from_numpy(np.ascontiguousarray(c[f"val{c['L']}"].T)).cuda()
+    for lv in (leaves, leaves.to(torch.uint8)):
+        post, hd = m.bp_cls(lv)
+        np.testing.assert_allclose(post.cpu().numpy(), c["cls_post"].T, rtol=RTOL, atol=1e-7)
+        ref_hd = c["cls_root_hd"].T
+        np.testing.assert_allclose(hd.cpu().numpy(), ref_hd, rtol=RTOL, atol=2e-5)
+
+
+@pytest.mark.parametrize("L,s,q,ti,B", [(4, 3, 10, True, 4099), (3, 4, 10, True, 1000), (6, 2, 7, False, 513),
+                                         (2, 8, 16, True, 300), (9, 2, 3, True, 200), (4, 3, 10, False, 777),
+                                         (1, 5, 12, True, 65), (3, 3, 2, True, 129)])
+def test_sampling_and_bp_vs_oracle(ops, L, s, q, ti, B):
+    """Seeded larger batches (ragged tails, n_L > 256 chunking, per-edge tables) against the oracle."""
+    from oracle import ghm_oracle as O
+    rng = np.random.RandomState(L * 100 + s * 10 + q)
+    np.random.seed(L * 1000 + s * 10 + q)
+    T = O.gen_transition(L, s, q, 0.2, 1.0, ti)
+    py = rng.dirichlet(np.ones(q) * 3)
+    root = rng.randint(0, q, size=B)
+    U = rng.rand(O.n_edges(L, s), B)
+    vals = O.sample_tree(T, L, s, q, B, root=root, U=U)
+    post, hd = O.bp_cls(T, vals[-1], L, s, q, py)
+    m = ops.GhmModel(T, L, s, q, p_y=py, device="cuda:0")
+    assert m.ti == ti
+    out = m.sample(B, root=root, U=torch.from_numpy(U).cuda())
+    assert np.array_equal(out["leaves"].cpu().numpy(), vals[-1].T)
+    p, h = m.bp_cls(out["leaves"])
+    np.testing.assert_allclose(p.cpu().numpy(), post.T, rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(h.cpu().numpy(), hd[0][0].T, rtol=RTOL, atol=2e-5)
+    assert m.status() == 0
+
+
+@pytest.mark.parametrize("L,s,q,ti,B", [(4, 3, 10, True, 1031), (3, 2, 5, False, 200), (2, 4, 16, True, 97)])
+def test_philox_sampling_bit_exact_vs_philox_oracle(ops, L, s, q, ti, B):
+    """Philox mode: leaves, roots and fused BP must match the NumPy Philox restatement exactly."""
+    from oracle import ghm_oracle as O, philox
+    np.random.seed(7)
+    T = O.gen_transition(L, s, q, 0.25, 1.0, ti)
+    py = np.random.dirichlet(np.ones(q) * 2)
+    m = ops.GhmModel(T, L, s, q, p_y=py, device="cuda:0")
+    seed, off = 0x1234ABCD5678, 1000003
+    for mode, kw in ((ops.ROOT_PRIOR, dict(p_y=py)), (ops.ROOT_UNIFORM, dict(root_uniform=True))):
+        vals = philox.sample_tree_philox(T, L, s, q, B, seed, tree_offset=off, **kw)
+        out = m.sample(B, seed=seed, tree_offset=off, root_mode=mode, want_post=True, want_root_hd=True)
+        assert np.array_equal(out["root"].cpu().numpy(), vals[0][0])
+        assert np.array_equal(out["leaves"].cpu().numpy(), vals[-1].T)
+        post, hd = O.bp_cls(T, vals[-1], L, s, q, py)
+        np.testing.assert_allclose(out["post"].cpu().numpy(), post.T, rtol=RTOL, atol=1e-7)
+        np.testing.assert_allclose(out["root_hd"].cpu().numpy(), hd[0][0].T, rtol=RTOL, atol=2e-5)
+    # sharding invariance: the same global trees drawn as two shards
+    a = m.sample(B // 2, seed=seed, tree_offset=off, root_mode=ops.ROOT_UNIFORM)
+    b = m.sample(B - B // 2, seed=seed, tree_offset=off + B // 2, root_mode=ops.ROOT_UNIFORM)
+    assert np.array_equal(torch.cat([a["leaves"], b["leaves"]]).cpu().numpy(), vals[-1].T)
+
+
+def test_philox_marginals_statistical(ops):
+    """Leaf marginals of 2M Philox trees against the analytic p_y * prod T (5 sigma)."""
+    from oracle import ghm_oracle as O
+    np.random.seed(5)
+    L, s, q, B = 3, 3, 10, 1 << 21
+    T = O.gen_transition(L, s, q, 0.2, 1.0, True)
+    py = np.random.dirichlet(np.ones(q) * 2)
+    m = ops.GhmModel(T, L, s, q, p_y=py, device="cuda:0")
+    out = m.sample(B, seed=11, leaf_dtype=torch.uint8)
+    lv = out["leaves"]
+    for leaf in (0, 13, 26):
+        p = py.copy()
+        idx = leaf
+        path = []
+        for l in range(L, 0, -1):
+            path.append((l - 1, idx))
+            idx //= s
+        for l, e in reversed(path):
+            p = p @ T[l][e]
+        emp = torch.bincount(lv[:, leaf].long(), minlength=q).cpu().numpy() / B
+        assert np.all(np.abs(emp - p) < 5 * np.sqrt(p * (1 - p) / B)), (leaf, emp, p)
+
+
+def test_clip_risk_vs_oracle(ops):
+    from oracle import ghm_oracle as O
+    rng = np.random.RandomState(0)
+    n, K, q = 1000, 4, 10
+    t = rng.dirichlet(np.ones(q) * 0.5, size=n * (K + 1)).astype(np.float32)
+    i = rng.dirichlet(np.ones(q) * 0.5, size=n * (K + 1)).astype(np.float32)
+    ref_mean, ref_se = O.clip_loss(t.T.astype(np.float64), i.T.astype(np.float64), n, K, q)
+    sums = ops.risk_clip(torch.from_numpy(t).cuda(), torch.from_numpy(i).cuda(), n, K, q)
+    mean, se = ops.mean_se(sums)
+    assert mean == pytest.approx(ref_mean, rel=1e-12) and se == pytest.approx(ref_se, rel=1e-9)
+    # sharded over pair ranges == whole
+    s2 = ops.new_sums("cuda:0")
+    for lo, hi in ((0, 333), (333, 1000)):
+        ops.risk_clip(torch.from_numpy(t).cuda(), torch.from_numpy(i).cuda(), n, K, q, sums=s2, pair_lo=lo, pair_hi=hi)
+    assert ops.mean_se(s2)[0] == pytest.approx(ref_mean, rel=1e-12)
+
+
+def test_host_clip_bayes_matches_device_path(ops):
+    """The host-buffer entry point == the same pipeline composed from device entry points."""
+    from oracle import ghm_oracle as O
+    u = np.ones(10) / 10
+    mo = O.PairedModel([4, 4], [3, 3], [u, u], [.2, .2])
+    tm = ops.GhmModel(mo.t_T, 4, 3, 10, device="cuda:0")
+    im = ops.GhmModel(mo.i_T, 4, 3, 10, device="cuda:0")
+    n, K, seed = 3000, 4, 77
+    B = n * (K + 1)
+    tl = torch.empty((B, 81), dtype=torch.int64).pin_memory()
+    il = torch.empty((B, 81), dtype=torch.int64).pin_memory()
+    tp = torch.empty((B, 10), dtype=torch.float32).pin_memory()
+    ip = torch.empty((B, 10), dtype=torch.float32).pin_memory()
+    sums = ops.host_clip_bayes(tm, im, n, K, seed=seed, leaves_out=(tl, il), pp_out=(tp, ip))
+    # device composition
+    t = tm.sample(B, seed=seed, root_mode=ops.ROOT_UNIFORM, want_post=True)
+    i1 = im.sample(2 * n, root=t["root"][:2 * n], seed=seed ^ ops.IMAGE_SEED_XOR, want_post=True)
+    i2 = im.sample((K - 1) * n, seed=seed ^ ops.IMAGE_SEED_XOR, tree_offset=2 * n, root_mode=ops.ROOT_UNIFORM,
+                   want_post=True)
+    assert torch.equal(t["leaves"].cpu(), tl)
+    assert torch.equal(torch.cat([i1["leaves"], i2["leaves"]]).cpu(), il)
+    ipp = torch.cat([i1["post"], i2["post"]])
+    assert torch.equal(t["post"].cpu(), tp) and torch.equal(ipp.cpu(), ip)
+    s2 = ops.risk_clip(t["post"], ipp, n, K, 10)
+    assert sums[2] == n and sums[0] == pytest.approx(float(s2[0]), rel=1e-12)
+    # and against the float64 oracle on the same leaves (BP parity at the risk level)
+    tpp, _ = O.bp_cls(mo.t_T, tl.numpy().T, 4, 3, 10, u)
+    ipp64, _ = O.bp_cls(mo.i_T, il.numpy().T, 4, 3, 10, u)
+    ref, _ = O.clip_loss(tpp, ipp64, n, K, 10)
+    assert sums[0] / n == pytest.approx(ref, rel=1e-5)
