@@ -1,0 +1,762 @@
+"""Call-compatible mirror of the reference module ``ghmclip.data.data_random_GHM``.
+
+Same public names, constructor / method signatures, return-tuple structure, shapes and dtypes
+as the reference (src/ghmclip/data/data_random_GHM.py; shape dump in SURVEY.md Appendix B), but
+sampling and every belief-propagation pass run in libghm_b200's sm_100a kernels.  There is no
+CPU fallback: constructing a tree or sampler without the CUDA library / a GPU raises.
+
+Two RNG modes
+  rng="numpy"  (default, PARITY): the host draws exactly what the reference draws from NumPy's
+      global legacy stream, in the reference's order (seed in the ctor, GenTransition, root
+      ``choice``, ``rand`` per edge, ``randn`` noise), uploads the uniforms and the f64-CDF sampler
+      kernel reproduces the reference's leaves bit-for-bit.  Downstream draws stay in lock-step.
+  rng="philox": roots, trees and noise are drawn on the device by Philox4x32-10 keyed with
+      (seed, global tree index); nothing random touches the host.  This is the throughput mode.
+
+Extra keyword arguments (all optional, defaults preserve reference behaviour):
+  device=  CUDA device used for the computation (default: current device)
+  rng=, seed=  as above.
+Deliberate deviations, each mirrored from SURVEY.md section 8 / Appendix A:
+  * ``GHMTree.T_value`` holds the root and the leaf level only (interior levels are ``None``): no
+    caller in the reference reads them and they never leave the SM in the fused kernel.
+  * ``Node`` objects exist for ``root_node`` / ``leaves_nodes`` only (no per-node message graph).
+  * ``BP_dummy_NWP`` / ``BP_NWP`` (dead code upstream, :223-334) raise NotImplementedError.
+"""
+import numpy as np
+import torch
+import torch.nn as nn  # noqa: F401  (the reference re-exports these through `import *`)
+from tqdm import tqdm  # noqa: F401
+
+from . import ops
+from .sharding import all_reduce_sums, dist_info, mean_se_from_sums, shard_range
+
+__all__ = ["PPCLIPLoss", "GenTransition", "Node", "GHMTree", "SingleSampler", "DoubleSampler",
+           "ClassificationSampler", "DenoiseSampler", "ClipSampler", "clip_loss_compute",
+           "ConditionalDenoiseSampler", "NextWordPredictSampler", "np", "torch", "nn", "tqdm"]
+
+
+def _cuda_device(device=None):
+    if device is None or (isinstance(device, str) and device == "cpu") or \
+            (isinstance(device, torch.device) and device.type == "cpu"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ghm_b200 needs a CUDA device: this path has no CPU fallback")
+        return torch.device("cuda", torch.cuda.current_device())
+    d = torch.device(device)
+    return torch.device("cuda", d.index if d.index is not None else torch.cuda.current_device())
+
+
+# ------------------------------------------------------------------------------------------
+# module-level functions
+# ------------------------------------------------------------------------------------------
+def _clip_loss_device(t_pp, i_pp, n_eval, K, variable_type, device=None):
+    """(q, n(K+1)) posteriors (numpy or torch) -> (mean, se) via the K6 kernel."""
+    dev = _cuda_device(device if device is not None else (t_pp.device if isinstance(t_pp, torch.Tensor) else None))
+    t = torch.as_tensor(np.asarray(t_pp) if not isinstance(t_pp, torch.Tensor) else t_pp)
+    i = torch.as_tensor(np.asarray(i_pp) if not isinstance(i_pp, torch.Tensor) else i_pp)
+    t = t.to(dev).T.to(torch.float32).contiguous()
+    i = i.to(dev).T.to(torch.float32).contiguous()
+    sums = ops.risk_clip(t, i, int(n_eval), int(K), int(variable_type))
+    mean, se = mean_se_from_sums(sums)
+    return np.float64(mean), np.float64(se)
+
+
+def PPCLIPLoss(t_pp, i_pp, n_eval, K=4, variable_type=10):
+    """Bayes CLIP objective from (q, n(K+1)) posteriors (reference :13-41)."""
+    return _clip_loss_device(t_pp, i_pp, n_eval, K, variable_type)
+
+
+def clip_loss_compute(ttree_pp, itree_pp, n_eval, K, variable_type):
+    """Same math as PPCLIPLoss (reference :819-844)."""
+    return _clip_loss_device(ttree_pp, itree_pp, n_eval, K, variable_type)
+
+
+def _softmax_row(x=np.array([[]])):
+    """Row softmax (reference :91-96); host-side, used once per sampler to build the tables."""
+    e_x = np.exp(x - np.max(x, axis=1, keepdims=True))
+    return e_x / e_x.sum(axis=1, keepdims=True)
+
+
+def GenTransition(n_layer, n_child, variable_type, p_flip=0.3, flip_scale=1.0, translation_invariance=True,
+                  verbose=False):
+    """Per-edge transition matrices from NumPy's global stream in the reference's draw order (:43-89).
+
+    Host-side one-off (microseconds next to a batch); the result is what ``ops.GhmModel`` uploads.
+    Returns list[n_layer] of list[n_child**(l+1)] of (q,q) float64; TI levels share the same objects.
+    """
+    q = variable_type
+    transition, skeleton = [], []
+    for layer in range(n_layer):
+        level = []
+        if translation_invariance:
+            skel = np.identity(q)[np.random.permutation(q), :]
+            shared = [(1 - p_flip) * skel + p_flip * _softmax_row(np.random.normal(0, flip_scale, [q, q]))
+                      for _ in range(n_child)]
+            for _ in range(n_child ** layer):
+                level.extend(shared)
+            skeleton.append(skel)
+        else:
+            for _ in range(n_child ** layer):
+                for _ in range(n_child):
+                    skel = np.identity(q)[np.random.permutation(q), :]
+                    level.append((1 - p_flip) * skel
+                                 + p_flip * _softmax_row(np.random.normal(0, flip_scale, [q, q])))
+        transition.append(level)
+    return (transition, skeleton) if verbose else transition
+
+
+# ------------------------------------------------------------------------------------------
+# device-model cache: one GhmModel per (transition list, p_y, device)
+# ------------------------------------------------------------------------------------------
+_MODEL_CACHE = {}
+_MODEL_CACHE_MAX = 64
+
+
+def _model_for(transition, n_layer, n_child, variable_type, p_y, device):
+    py = None if p_y is None else np.asarray(p_y, dtype=np.float64)
+    key = (id(transition), device.index, None if py is None else py.tobytes())
+    hit = _MODEL_CACHE.get(key)
+    if hit is not None and hit[0] is transition:
+        return hit[1]
+    model = ops.GhmModel(transition, n_layer, n_child, variable_type, p_y=py, device=device)
+    if len(_MODEL_CACHE) >= _MODEL_CACHE_MAX:
+        _MODEL_CACHE.pop(next(iter(_MODEL_CACHE)))
+    _MODEL_CACHE[key] = (transition, model)      # the strong ref keeps id(transition) valid
+    return model
+
+
+# ------------------------------------------------------------------------------------------
+# tree
+# ------------------------------------------------------------------------------------------
+class Node:
+    """Lightweight node (reference :100-110).  Only root / leaf nodes are materialised here."""
+
+    def __init__(self, value=None, parent=None, children=None):
+        self.value = value
+        self.parent = parent
+        self.children = children
+        self.hd_message = 0
+
+
+class _LeafColumns:
+    """``T_value[-1]``: n_L per-leaf value lists, materialised lazily from the device tensor.
+
+    Behaves like the reference's list of lists: ``len``, iteration, ``[k]`` -> Python list of B
+    ints, item assignment (marks the tree dirty so ``build_tree`` re-uploads), ``np.array(x)``.
+    """
+
+    def __init__(self, dev_leaves):
+        self._dev = dev_leaves          # [B, n_L] device tensor (int64)
+        self._host = None               # (n_L, B) int64 ndarray, lazily
+        self.dirty = False
+
+    def _np(self):
+        if self._host is None:
+            self._host = np.ascontiguousarray(self._dev.cpu().numpy().T)
+        return self._host
+
+    def __len__(self):
+        return self._dev.shape[1]
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [row.tolist() for row in self._np()[k]]
+        return self._np()[k].tolist()
+
+    def __setitem__(self, k, v):
+        arr = self._np()
+        if not arr.flags.writeable:
+            self._host = arr = arr.copy()
+        arr[k] = np.asarray(v, dtype=np.int64)
+        self.dirty = True
+
+    def __iter__(self):
+        return (row.tolist() for row in self._np())
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._np()
+        return a.astype(dtype) if dtype is not None else a
+
+
+class GHMTree:
+    """Sampled GHM tree + exact BP (reference :112-613), backed by device tensors.
+
+    Device state: ``_leaves`` int64 [B, n_L], ``_root`` int64 [B], after BP: ``_post`` / ``_root_hd``
+    f32 [B, q], ``_mean`` f32 [B, n_L].  NumPy views are materialised on attribute access.
+    """
+
+    def __init__(self, n_layer=4, n_child=3, variable_type=10, p_y=np.ones(10) / 10, p_flip=0.3, transition=None,
+                 batch_size=128, build_tree=False, root=None, device=None, rng="numpy", seed=0, tree_offset=0,
+                 _model=None):
+        self.variable_type = variable_type
+        self.posterior_probability_CLS = None
+        self.posterior_mean_DNS = None
+        self.n_layer = n_layer
+        self.n_child = n_child
+        self.p_y = p_y
+        self.p_flip = p_flip
+        self.transition = transition
+        self.batch_size = batch_size
+        self.root = root
+        self.build_tree_flag = build_tree
+        self.dns_flag = False
+        self.cls_flag = False
+        self.device = _cuda_device(device)
+        self.rng, self.seed, self.tree_offset = rng, seed, tree_offset
+        self._model_hint = _model
+        self._root_hd = None          # device f32 [B, q]; root_node.hd_message
+        self._root_hd_host = None     # numpy override (after BP_DNS: hd + ext, reference aliasing :504-506)
+        self._post = self._mean = None
+        self._dns_state = None        # (z, sigma, ext) of the last BP_DNS, for guided_info
+        self._cls_guides = None
+        self.gen_values()
+        if self.build_tree_flag:
+            self.build_tree()
+
+    # -- model -------------------------------------------------------------------------
+    @property
+    def model(self):
+        m = self._model_hint
+        if m is not None and getattr(m, "_transition_ref", None) is self.transition:
+            return m
+        m = _model_for(self.transition, self.n_layer, self.n_child, self.variable_type, self.p_y, self.device)
+        m._transition_ref = self.transition
+        self._model_hint = m
+        return m
+
+    # -- sampling (reference gen_values, :145-165) ----------------------------------------
+    def gen_values(self):
+        m = self.model
+        B = self.batch_size
+        if self.rng == "numpy":
+            root = self.root
+            if root is None:
+                root = np.random.choice(self.variable_type, size=B, p=self.p_y)
+            root = np.asarray(root)
+            # one rand(E, B) == the reference's E sequential rand(B, 1) calls (same stream)
+            U = np.random.rand(m.n_edges, B)
+            out = m.sample(B, root=torch.from_numpy(root.astype(np.int64)), U=torch.from_numpy(U))
+            root_host = root
+        elif self.rng == "philox":
+            if self.root is not None:
+                out = m.sample(B, root=torch.as_tensor(self.root), seed=self.seed, tree_offset=self.tree_offset)
+            else:
+                out = m.sample(B, seed=self.seed, tree_offset=self.tree_offset, root_mode=ops.ROOT_PRIOR)
+            root_host = None
+        else:
+            raise ValueError("rng must be 'numpy' or 'philox'")
+        self._leaves = out["leaves"]
+        self._root = out["root"]
+        self._root_host = root_host
+        self.T_value = [[self._root_np()]] + [None] * (self.n_layer - 1) + [_LeafColumns(self._leaves)]
+
+    def _root_np(self):
+        if self._root_host is None:
+            self._root_host = self._root.cpu().numpy()
+        return self._root_host
+
+    # -- (re)build: pick up caller edits of T_value (reference build_tree, :167-183) -----------
+    def build_tree(self):
+        self.posterior_probability_CLS = None
+        self.posterior_mean_DNS = None
+        self._post = self._mean = self._root_hd = self._root_hd_host = None
+        self._cls_guides = None
+        lv = self.T_value[-1]
+        if not isinstance(lv, _LeafColumns) or lv.dirty or lv._dev is not self._leaves:
+            arr = np.asarray(lv, dtype=np.int64)                      # (n_L, B)
+            if arr.ndim != 2 or arr.shape[0] != self.n_child ** self.n_layer:
+                raise ValueError("T_value[-1] must hold %d leaf columns" % (self.n_child ** self.n_layer))
+            self._leaves = torch.from_numpy(np.ascontiguousarray(arr.T)).to(self.device)
+            self.batch_size = arr.shape[1]
+            cols = _LeafColumns(self._leaves)
+            cols._host = arr
+            self.T_value[-1] = cols
+        r0 = self.T_value[0][0]
+        if r0 is not self._root_host:
+            self._root_host = np.asarray(r0)
+            self._root = torch.from_numpy(self._root_host.astype(np.int64)).to(self.device)
+        self.Tree = None
+
+    # -- BP: root posterior (reference BP_CLS, :185-221) --------------------------------------
+    def BP_CLS(self):
+        self._post, self._root_hd = self.model.bp_cls(self._leaves)
+        self._root_hd_host = None
+        self.posterior_probability_CLS = self._post.T.double().cpu().numpy()
+        self.cls_flag = True
+        return self.posterior_probability_CLS
+
+    # -- BP: Gaussian denoiser (reference BP_DNS, :467-523) -------------------------------------
+    def _to_dev_bq(self, ext):
+        """external message (q,B) numpy/torch -> device f32 [B,q]."""
+        if ext is None:
+            return None
+        e = ext if isinstance(ext, torch.Tensor) else torch.from_numpy(np.asarray(ext))
+        return e.to(self.device).T.to(torch.float32).contiguous()
+
+    def BP_DNS(self, z, sigma=1.0, external_hd_message=None):
+        zz = z if isinstance(z, torch.Tensor) else torch.from_numpy(np.asarray(z))
+        zd = zz.to(self.device).T.to(torch.float32).contiguous()              # [B, n_L]
+        ext = self._to_dev_bq(external_hd_message)
+        self._mean = self.model.bp_dns(zd, float(sigma), ext)
+        self._dns_state = (zd, float(sigma), ext)
+        self.posterior_mean_DNS = self._mean.T.double().cpu().numpy()
+        self.dns_flag = True
+        return self.posterior_mean_DNS
+
+    # -- BP: next-token posterior (reference BP_NWP_autoregressive, :336-463) -------------------
+    def BP_NWP_autoregressive(self, guide_info=False, device="cpu", external_hd_message=None, verbose=False, pos=3):
+        ext = self._to_dev_bq(external_hd_message)
+        if guide_info:
+            guides, pp = self.model.guides_nwp(self._leaves, ext)
+            guides = [g.to(device) for g in guides]
+        else:
+            pp, guides = self.model.bp_nwp(self._leaves, ext), []
+        return pp.to(device), guides
+
+    def BP_dummy_NWP(self, position, external_hd_message=None):
+        raise NotImplementedError("BP_dummy_NWP is dead code upstream (reference :223-272); "
+                                  "use BP_NWP_autoregressive (no CPU fallback is provided)")
+
+    def BP_NWP(self, position, external_hd_message=None):
+        raise NotImplementedError("BP_NWP is dead code upstream (reference :274-334); "
+                                  "use BP_NWP_autoregressive (no CPU fallback is provided)")
+
+    # -- guide tensors (reference guided_info, :526-592) ---------------------------------------
+    def guided_info(self, device="cpu"):
+        if self.cls_flag:
+            guides, post, hd = self.model.guides_cls(self._leaves)
+        elif self.dns_flag:
+            z, sigma, ext = self._dns_state
+            guides, _ = self.model.guides_dns(z, sigma, ext)
+        else:
+            return []
+        return [g.to(device) for g in guides]
+
+    # -- properties (reference :595-613) ----------------------------------------------------
+    @property
+    def root_node(self):
+        node = Node(self.root_value)
+        if self._root_hd is not None:       # (q, B) float64: the cross-modal "external" message (:871,919)
+            if self._root_hd_host is None:
+                self._root_hd_host = self._root_hd.T.double().cpu().numpy()
+            node.hd_message = self._root_hd_host
+        return node
+
+    @property
+    def leaves_nodes(self):
+        return [Node(v) for v in self.T_value[-1]]
+
+    @property
+    def leaves_values(self):
+        return self.T_value[-1]
+
+    @property
+    def root_value(self):
+        return self.T_value[0][0]
+
+
+# ------------------------------------------------------------------------------------------
+# samplers (reference :617-942)
+# ------------------------------------------------------------------------------------------
+class _SamplerBase:
+    def _init_backend(self, device, rng, seed):
+        self.device = _cuda_device(device)
+        if rng not in ("numpy", "philox"):
+            raise ValueError("rng must be 'numpy' or 'philox'")
+        self.rng, self.seed = rng, int(seed)
+        self.tree_offset = 0          # global index of the next Philox tree (explicit, resumable RNG state)
+
+    def _advance(self, n):
+        off = self.tree_offset
+        self.tree_offset += int(n)
+        return off
+
+
+class SingleSampler(_SamplerBase):
+    """Single-tree sampler (reference :617-639)."""
+
+    def __init__(self, n_layer, n_child, p_y, p_flip, flip_scale=1.0, variable_type=10, translation_invariance=True,
+                 seedtree=42, device=None, rng="numpy", seed=1234):
+        self.n_layer, self.n_child, self.p_y, self.p_flip = n_layer, n_child, p_y, p_flip
+        self.variable_type, self.translation_invariance = variable_type, translation_invariance
+        self.seedtree, self.flip_scale = seedtree, flip_scale
+        self._init_backend(device, rng, seed)
+        np.random.seed(seedtree)
+        self.transition = GenTransition(n_layer, n_child, variable_type, p_flip, flip_scale,
+                                        translation_invariance=translation_invariance)
+        self.model = ops.GhmModel(self.transition, n_layer, n_child, variable_type, p_y=p_y, device=self.device)
+        self.model._transition_ref = self.transition
+
+    def _tree(self, batch_size, root=None):
+        return GHMTree(self.n_layer, self.n_child, self.variable_type, self.p_y, self.p_flip, self.transition,
+                       batch_size, build_tree=True, root=root, device=self.device, rng=self.rng, seed=self.seed,
+                       tree_offset=self._advance(batch_size) if self.rng == "philox" else 0, _model=self.model)
+
+    def get_batch(self, batch_size=128):
+        T = self._tree(batch_size)
+        return T.T_value[0][0], T.T_value[-1][0]
+
+
+class DoubleSampler(_SamplerBase):
+    """Paired text/image sampler (reference :641-682)."""
+
+    def __init__(self, n_layers, n_childs, p_ys, p_flips, flip_scale=1, variable_type=10, translation_invariance=True,
+                 seedtree=42, device=None, rng="numpy", seed=1234):
+        self.n_layers, self.n_childs, self.p_ys, self.p_flips = n_layers, n_childs, p_ys, p_flips
+        self.flip_scale, self.variable_type, self.seedtree = flip_scale, variable_type, seedtree
+        self._init_backend(device, rng, seed)
+        np.random.seed(seedtree)
+        self.t_transition = GenTransition(n_layers[0], n_childs[0], variable_type, p_flips[0], flip_scale,
+                                          translation_invariance=translation_invariance)
+        self.i_transition = GenTransition(n_layers[1], n_childs[1], variable_type, p_flips[1], flip_scale,
+                                          translation_invariance=translation_invariance)
+        self.t_model = ops.GhmModel(self.t_transition, n_layers[0], n_childs[0], variable_type, p_y=p_ys[0],
+                                    device=self.device)
+        self.i_model = ops.GhmModel(self.i_transition, n_layers[1], n_childs[1], variable_type, p_y=p_ys[1],
+                                    device=self.device)
+        self.t_model._transition_ref = self.t_transition
+        self.i_model._transition_ref = self.i_transition
+
+    # modality 0 = text, 1 = image; the image modality draws from an independent Philox key
+    def _tree(self, which, batch_size, root=None, tree_offset=0):
+        tr, mo = (self.t_transition, self.t_model) if which == 0 else (self.i_transition, self.i_model)
+        seed = self.seed if which == 0 else self.seed ^ ops.IMAGE_SEED_XOR
+        return GHMTree(self.n_layers[which], self.n_childs[which], self.variable_type, self.p_ys[which],
+                       self.p_flips[which], tr, batch_size, build_tree=True, root=root, device=self.device,
+                       rng=self.rng, seed=seed, tree_offset=tree_offset, _model=mo)
+
+    def _shared_root(self, batch_size, off):
+        """np.random.choice(q, size=B): uniform, ignores p_ys (reference :674,758,858,906)."""
+        if self.rng == "numpy":
+            return np.random.choice(self.variable_type, size=batch_size)
+        return None
+
+    def _paired_trees(self, batch_size):
+        off = self._advance(batch_size) if self.rng == "philox" else 0
+        if self.rng == "numpy":
+            root = np.random.choice(self.variable_type, size=batch_size)
+            text_tree = self._tree(0, batch_size, root=root)
+            image_tree = self._tree(1, batch_size, root=root)
+        else:
+            out = self.t_model.sample(batch_size, seed=self.seed, tree_offset=off, root_mode=ops.ROOT_UNIFORM)
+            text_tree = _tree_from_device(self, 0, out, batch_size)
+            iout = self.i_model.sample(batch_size, root=out["root"], seed=self.seed ^ ops.IMAGE_SEED_XOR,
+                                       tree_offset=off)
+            image_tree = _tree_from_device(self, 1, iout, batch_size)
+            root = None
+        return root, text_tree, image_tree
+
+    def get_batch(self, batch_size=128):
+        off = self._advance(batch_size) if self.rng == "philox" else 0
+        text_tree = self._tree(0, batch_size, tree_offset=off)
+        image_tree = self._tree(1, batch_size, tree_offset=off)
+        return text_tree.T_value[0][0], image_tree.T_value[0][0], text_tree.T_value[-1][0], image_tree.T_value[-1][0]
+
+    def get_zeroshot_batch(self, batch_size=128, return_tree=False):
+        root_tree, text_tree, image_tree = self._paired_trees(batch_size)
+        text_tree.BP_CLS()
+        image_tree.BP_CLS()
+        if return_tree:
+            return text_tree, image_tree
+        return (np.array(text_tree.leaves_values).T, np.array(image_tree.leaves_values).T,
+                np.array(text_tree.posterior_probability_CLS).T, np.array(image_tree.posterior_probability_CLS).T,
+                np.array(text_tree.root_value))
+
+
+def _tree_from_device(sampler, which, out, batch_size):
+    """Wrap already-sampled device tensors (Philox path) in a GHMTree without re-sampling."""
+    t = GHMTree.__new__(GHMTree)
+    tr, mo = (sampler.t_transition, sampler.t_model) if which == 0 else (sampler.i_transition, sampler.i_model)
+    t.variable_type = sampler.variable_type
+    t.posterior_probability_CLS = t.posterior_mean_DNS = None
+    t.n_layer, t.n_child = sampler.n_layers[which], sampler.n_childs[which]
+    t.p_y, t.p_flip, t.transition = sampler.p_ys[which], sampler.p_flips[which], tr
+    t.batch_size, t.root, t.build_tree_flag = batch_size, None, True
+    t.dns_flag = t.cls_flag = False
+    t.device, t.rng, t.seed, t.tree_offset = sampler.device, sampler.rng, sampler.seed, 0
+    t._model_hint = mo
+    t._root_hd = t._root_hd_host = t._post = t._mean = t._dns_state = t._cls_guides = None
+    t._leaves, t._root, t._root_host = out["leaves"], out["root"], None
+    t.T_value = [[t._root_np()]] + [None] * (t.n_layer - 1) + [_LeafColumns(t._leaves)]
+    t.Tree = None
+    return t
+
+
+class ClassificationSampler(SingleSampler):
+    """Root classification from all leaves (reference :685-720)."""
+
+    def __init__(self, n_layer, n_child, p_y, p_flip=0.3, flip_scale=1, variable_type=10, translation_invariance=True,
+                 seedtree=42, device=None, rng="numpy", seed=1234):
+        super().__init__(n_layer, n_child, p_y, p_flip, flip_scale, variable_type, translation_invariance, seedtree,
+                         device=device, rng=rng, seed=seed)
+
+    def get_batch(self, batch_size=128, guide=False, device="cpu"):
+        tree = self._tree(batch_size)
+        leaves_values = tree._leaves.to(device)
+        root_values = tree._root.to(device)
+        if guide:
+            tree.BP_CLS()
+            guided_info = tree.guided_info(device=device)
+        else:
+            guided_info = None
+        if tree.posterior_probability_CLS is None:
+            # the reference evaluates `None.T` here (:705) -> AttributeError; keep the error behaviour
+            raise AttributeError("'NoneType' object has no attribute 'T' (ClassificationSampler.get_batch needs guide=True)")
+        return leaves_values, root_values, guided_info, tree.posterior_probability_CLS.T
+
+    def get_Bayes(self, n_eval=10000):
+        """Bayes CE of the root (reference :707-720): float32 loss, torch.std (unbiased) / sqrt(n)."""
+        tree = self._tree(n_eval)
+        tree.BP_CLS()
+        sums = ops.risk_ce(tree._post, tree._root)
+        s1, s2, c = (float(x) for x in sums.tolist())
+        mean = s1 / c
+        var = max((s2 - c * mean * mean) / max(c - 1, 1), 0.0)
+        return mean, (var ** 0.5) / np.sqrt(n_eval)
+
+
+class DenoiseSampler(SingleSampler):
+    """Denoising noisy leaves of one tree (reference :722-742)."""
+
+    def __init__(self, n_layer, n_child, p_y, p_flip=0.3, sigma=1, flip_scale=1, variable_type=10,
+                 translation_invariance=True, seedtree=42, device=None, rng="numpy", seed=1234):
+        super().__init__(n_layer, n_child, p_y, p_flip, flip_scale, variable_type, translation_invariance, seedtree,
+                         device=device, rng=rng, seed=seed)
+        self.sigma = sigma
+
+    def get_batch(self, batch_size=128, guide=False, device="cpu"):
+        tree = self._tree(batch_size)
+        if self.rng == "numpy":
+            zs = np.random.randn(self.n_child ** self.n_layer, batch_size) * self.sigma + np.asarray(tree.leaves_values)
+            zs_dev = torch.from_numpy(zs).to(self.device).T.to(torch.float32).contiguous()
+        else:
+            zs_dev = self.model.gauss_noise(tree._leaves, self.sigma, seed=self.seed, tree_offset=tree.tree_offset)
+            zs = zs_dev.T
+        xs = tree._leaves.to(torch.float32).to(device)
+        if guide:
+            tree.BP_DNS(zs, self.sigma)
+            guided_info = tree.guided_info()            # reference does not forward `device` here (:737)
+        else:
+            guided_info = None
+        if tree.posterior_mean_DNS is None:
+            raise AttributeError("'NoneType' object has no attribute 'T' (DenoiseSampler.get_batch needs guide=True)")
+        return zs_dev.to(device), xs, guided_info, tree.posterior_mean_DNS.T
+
+
+class ClipSampler(DoubleSampler):
+    """Matched / mismatched pairs for the K-way CLIP objective (reference :746-817)."""
+
+    def __init__(self, n_layers, n_childs, p_ys, p_flips, K=4, flip_scale=1, variable_type=10,
+                 translation_invariance=True, seedtree=42, device=None, rng="numpy", seed=1234):
+        super().__init__(n_layers, n_childs, p_ys, p_flips, flip_scale, variable_type, translation_invariance,
+                         seedtree, device=device, rng=rng, seed=seed)
+        self.K = K
+
+    def _sample_layout(self, batch_size, want_leaves=True, want_post=False, pair_lo=0, pair_hi=None):
+        """Device-side sampling of the block layout [match1 | match2 | K-1 negatives] (:758-764).
+
+        Returns dict(t=..., i=...) of ops.sample outputs (``post`` fused in Philox mode when asked).
+        Philox mode draws block ``j`` of pairs [pair_lo, pair_hi) only (multi-GPU sharding on the pair
+        index; global tree index = offset + j*n + pair).
+        """
+        n, K, q = batch_size, self.K, self.variable_type
+        B = n * (K + 1)
+        if self.rng == "numpy":
+            text_root = np.random.choice(q, size=n * (K + 1))
+            image_root = np.random.choice(q, size=n * (K - 1))
+            image_root = np.append(text_root[:2 * n], image_root)
+            Ut = np.random.rand(self.t_model.n_edges, B)
+            Ui = np.random.rand(self.i_model.n_edges, B)
+            t = self.t_model.sample(B, root=torch.from_numpy(text_root.astype(np.int64)), U=torch.from_numpy(Ut))
+            i = self.i_model.sample(B, root=torch.from_numpy(image_root.astype(np.int64)), U=torch.from_numpy(Ui))
+            if want_post:
+                t["post"], t["root_hd"] = self.t_model.bp_cls(t["leaves"])
+                i["post"], i["root_hd"] = self.i_model.bp_cls(i["leaves"])
+            return {"t": t, "i": i, "n_local": n}
+        pair_hi = n if pair_hi is None else pair_hi
+        nl = pair_hi - pair_lo
+        off = self._advance(B)
+        dev = self.device
+        if nl == n:      # whole layout on this device: 3 launches over contiguous global tree ranges
+            t = {"leaves": torch.empty((B, self.t_model.n_leaves), dtype=torch.int64, device=dev) if want_leaves else None,
+                 "root": torch.empty(B, dtype=torch.int64, device=dev),
+                 "post": torch.empty((B, q), dtype=torch.float32, device=dev) if want_post else None}
+            i = {"leaves": torch.empty((B, self.i_model.n_leaves), dtype=torch.int64, device=dev) if want_leaves else None,
+                 "root": torch.empty(B, dtype=torch.int64, device=dev),
+                 "post": torch.empty((B, q), dtype=torch.float32, device=dev) if want_post else None}
+            iseed = self.seed ^ ops.IMAGE_SEED_XOR
+            cut = lambda x, a, b: None if x is None else x[a:b]
+            ops.sample_into(self.t_model, B, ops.ROOT_UNIFORM, None, self.seed, off, t["root"], t["leaves"], t["post"], None)
+            ops.sample_into(self.i_model, 2 * n, ops.ROOT_GIVEN, t["root"][:2 * n], iseed, off, cut(i["root"], 0, 2 * n),
+                            cut(i["leaves"], 0, 2 * n), cut(i["post"], 0, 2 * n), None)
+            ops.sample_into(self.i_model, (K - 1) * n, ops.ROOT_UNIFORM, None, iseed, off + 2 * n, cut(i["root"], 2 * n, B),
+                            cut(i["leaves"], 2 * n, B), cut(i["post"], 2 * n, B), None)
+            return {"t": t, "i": i, "n_local": n}
+        Bl = nl * (K + 1)
+        t = {"leaves": torch.empty((Bl, self.t_model.n_leaves), dtype=torch.int64, device=dev) if want_leaves else None,
+             "root": torch.empty(Bl, dtype=torch.int64, device=dev),
+             "post": torch.empty((Bl, q), dtype=torch.float32, device=dev) if want_post else None}
+        i = {"leaves": torch.empty((Bl, self.i_model.n_leaves), dtype=torch.int64, device=dev) if want_leaves else None,
+             "root": torch.empty(Bl, dtype=torch.int64, device=dev),
+             "post": torch.empty((Bl, q), dtype=torch.float32, device=dev) if want_post else None}
+        iseed = self.seed ^ ops.IMAGE_SEED_XOR
+
+        def sl(x, j):
+            return None if x is None else x[j * nl:(j + 1) * nl]
+        for j in range(K + 1):
+            goff = off + j * n + pair_lo
+            ops.sample_into(self.t_model, nl, ops.ROOT_UNIFORM, None, self.seed, goff, sl(t["root"], j),
+                            sl(t["leaves"], j), sl(t["post"], j), None)
+            if j < 2:
+                ops.sample_into(self.i_model, nl, ops.ROOT_GIVEN, sl(t["root"], j), iseed, goff, sl(i["root"], j),
+                                sl(i["leaves"], j), sl(i["post"], j), None)
+            else:
+                ops.sample_into(self.i_model, nl, ops.ROOT_UNIFORM, None, iseed, goff, sl(i["root"], j),
+                                sl(i["leaves"], j), sl(i["post"], j), None)
+        return {"t": t, "i": i, "n_local": nl}
+
+    def get_batch(self, device="cpu", batch_size=128, guide=False):
+        r = self._sample_layout(batch_size, want_leaves=True, want_post=False)
+        t, i = r["t"], r["i"]
+        if guide:
+            tg, t_post, _ = self.t_model.guides_cls(t["leaves"])
+            ig, i_post, _ = self.i_model.guides_cls(i["leaves"])
+            text_guided_info = [g.to(device) for g in tg]
+            image_guided_info = [g.to(device) for g in ig]
+            t_pp = t_post.double().cpu().numpy()
+            i_pp = i_post.double().cpu().numpy()
+        else:
+            text_guided_info = image_guided_info = t_pp = i_pp = None
+        return [t["leaves"].to(device), t["root"].to(device), text_guided_info, t_pp], \
+               [i["leaves"].to(device), i["root"].to(device), image_guided_info, i_pp]
+
+    def get_Bayes(self, n_eval=10000, distributed=False, group=None):
+        """Bayes CLIP loss (reference :786-817).  ``distributed=True`` (Philox only) shards the pair index
+        over the initialised process group and all-reduces the 24-byte risk sums."""
+        K, q = self.K, self.variable_type
+        if distributed:
+            if self.rng != "philox":
+                raise ValueError("distributed get_Bayes needs rng='philox' (the NumPy stream is serial)")
+            rank, world = dist_info(group)
+            lo, hi = shard_range(n_eval, rank, world)
+        else:
+            lo, hi = 0, n_eval
+        r = self._sample_layout(n_eval, want_leaves=False, want_post=True, pair_lo=lo, pair_hi=hi)
+        nl = r["n_local"]
+        sums = ops.new_sums(self.device)
+        if nl > 0:
+            ops.risk_clip(r["t"]["post"], r["i"]["post"], nl, K, q, sums=sums)
+        if distributed:
+            all_reduce_sums(sums, group)
+        mean, se = mean_se_from_sums(sums)
+        return np.float64(mean), np.float64(se)
+
+
+class ConditionalDenoiseSampler(DoubleSampler):
+    """Denoise image leaves conditioned on text (reference :846-894)."""
+
+    def __init__(self, n_layers, n_childs, p_ys, p_flips, sigma=1, flip_scale=1, variable_type=10,
+                 translation_invariance=True, seedtree=42, device=None, rng="numpy", seed=1234):
+        super().__init__(n_layers, n_childs, p_ys, p_flips, flip_scale, variable_type, translation_invariance,
+                         seedtree, device=device, rng=rng, seed=seed)
+        self.sigma = sigma
+
+    def _run(self, batch_size):
+        """sample pair -> noise -> text BP_CLS -> ext -> image BP_DNS; everything stays on the device."""
+        _, text_tree, image_tree = self._paired_trees(batch_size)
+        nLi = self.n_childs[1] ** self.n_layers[1]
+        if self.rng == "numpy":
+            noise = np.random.randn(nLi, batch_size) * self.sigma + np.asarray(image_tree.leaves_values)
+            z = torch.from_numpy(noise).to(self.device).T.to(torch.float32).contiguous()
+        else:
+            z = self.i_model.gauss_noise(image_tree._leaves, self.sigma, seed=self.seed ^ ops.IMAGE_SEED_XOR,
+                                         tree_offset=self.tree_offset - batch_size)
+        t_post, t_hd = self.t_model.bp_cls(text_tree._leaves)
+        mean = self.i_model.bp_dns(z, float(self.sigma), t_hd)
+        return text_tree, image_tree, z, t_post, t_hd, mean
+
+    def get_batch(self, batch_size=128, device="cpu", guide=False):
+        text_tree, image_tree, z, t_post, t_hd, mean = self._run(batch_size)
+        if guide:
+            tg, _, _ = self.t_model.guides_cls(text_tree._leaves)
+            ig, _ = self.i_model.guides_dns(z, float(self.sigma), t_hd)
+            text_guided_info = [g.to(device) for g in tg]
+            image_guided_info = [g.to(device) for g in ig]
+        else:
+            text_guided_info = image_guided_info = None
+        return (text_tree._leaves.to(device), text_tree._root.to(device), text_guided_info,
+                t_post.T.double().cpu().numpy()), \
+               (z.to(device), image_tree._leaves.to(device), image_guided_info, mean.double().cpu().numpy())
+
+    def get_Bayes(self, n_eval=30000, distributed=False, group=None):
+        """Bayes MSE (reference :886-894): mean_b sum_leaf (m - x)^2 and np.std / sqrt(n)."""
+        if distributed:
+            if self.rng != "philox":
+                raise ValueError("distributed get_Bayes needs rng='philox'")
+            rank, world = dist_info(group)
+            lo, hi = shard_range(n_eval, rank, world)
+            base = self._advance(n_eval)
+            self.tree_offset = base + lo
+            n_loc = hi - lo
+        else:
+            n_loc = n_eval
+        sums = ops.new_sums(self.device)
+        if n_loc > 0:
+            _, image_tree, _, _, _, mean = self._run(n_loc)
+            ops.risk_cdm(mean, image_tree._leaves, sums=sums)
+        if distributed:
+            self.tree_offset = base + n_eval
+            all_reduce_sums(sums, group)
+        mean_v, se = mean_se_from_sums(sums)
+        return np.float64(mean_v), np.float64(se)
+
+
+class NextWordPredictSampler(DoubleSampler):
+    """Image-conditioned next-word prediction (reference :896-942)."""
+
+    def __init__(self, n_layers, n_childs, p_ys, p_flips, flip_scale=1, variable_type=10, translation_invariance=True,
+                 seedtree=42, device=None, rng="numpy", seed=1234):
+        super().__init__(n_layers, n_childs, p_ys, p_flips, flip_scale, variable_type, translation_invariance,
+                         seedtree, device=device, rng=rng, seed=seed)
+
+    def get_batch(self, batch_size=128, device="cpu", guide=False):
+        _, text_tree, image_tree = self._paired_trees(batch_size)
+        text_leaves = text_tree._leaves.to(device)
+        if guide:
+            ig, i_post, i_hd = self.i_model.guides_cls(image_tree._leaves)
+            tg, pp = self.t_model.guides_nwp(text_tree._leaves, i_hd)
+            image_guided_info = [g.to(device) for g in ig]
+            text_guided_info = [g.to(device) for g in tg]
+        else:
+            i_post, i_hd = self.i_model.bp_cls(image_tree._leaves)
+            pp = self.t_model.bp_nwp(text_tree._leaves, i_hd)
+            image_guided_info = text_guided_info = None
+        return (text_leaves[:, :-1], text_leaves[:, 1:], text_guided_info, pp.to(device)), \
+               (image_tree._leaves.to(device), image_tree._root.to(device), image_guided_info,
+                i_post.double().cpu().numpy())
+
+    def get_Bayes(self, n_eval=30000, distributed=False, group=None):
+        """Bayes token CE (reference :931-942): float32 mean; "SE" = torch.std / sqrt(n_eval) (sic)."""
+        if distributed:
+            if self.rng != "philox":
+                raise ValueError("distributed get_Bayes needs rng='philox'")
+            rank, world = dist_info(group)
+            lo, hi = shard_range(n_eval, rank, world)
+            base = self._advance(n_eval)
+            self.tree_offset = base + lo
+            n_loc = hi - lo
+        else:
+            n_loc = n_eval
+        sums = ops.new_sums(self.device)
+        if n_loc > 0:
+            _, text_tree, image_tree = self._paired_trees(n_loc)
+            _, i_hd = self.i_model.bp_cls(image_tree._leaves)
+            pp = self.t_model.bp_nwp(text_tree._leaves, i_hd)
+            nL = self.t_model.n_leaves
+            ops.risk_ce(pp, text_tree._leaves, sums=sums, target_stride=nL, target_offset=1, row_group=nL - 1)
+        if distributed:
+            self.tree_offset = base + n_eval
+            all_reduce_sums(sums, group)
+        s1, s2, c = (float(x) for x in sums.tolist())
+        mean = s1 / c
+        var = max((s2 - c * mean * mean) / max(c - 1, 1), 0.0)          # torch.std is the unbiased estimator
+        return torch.tensor(mean, dtype=torch.float32), torch.tensor((var ** 0.5) / np.sqrt(n_eval), dtype=torch.float32)

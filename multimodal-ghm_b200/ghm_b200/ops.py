@@ -128,6 +128,94 @@ class GhmModel:
             check(self._lib.ghm_bp_cls(self._h, B, _ptr(leaves), _leaf_code(leaves), _ptr(post), _ptr(hd), _stream()))
         return post, hd
 
+    # ---- K3 ---------------------------------------------------------------------------
+    def _workspace(self, nbytes):
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < nbytes:
+            self._ws = ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
+        return ws
+
+    def bp_dns(self, z, sigma, ext=None):
+        """z f32 [B,n_L], ext f32 [B,q] or None -> posterior mean f32 [B,n_L]  (reference BP_DNS, :467-523)."""
+        z = z.contiguous()
+        B = z.shape[0]
+        assert z.dtype == torch.float32 and z.shape[1] == self.n_leaves and z.device == self.device
+        if ext is not None:
+            ext = ext.contiguous()
+            assert ext.dtype == torch.float32 and tuple(ext.shape) == (B, self.q)
+        with torch.cuda.device(self.device):
+            mean = torch.empty((B, self.n_leaves), dtype=torch.float32, device=self.device)
+            ws = self._workspace(self._lib.ghm_bp_dns_workspace_bytes(self._h, B))
+            check(self._lib.ghm_bp_dns(self._h, B, _ptr(z), float(sigma), _ptr(ext), _ptr(mean), _ptr(ws), _stream()))
+        return mean
+
+    # ---- K4 ---------------------------------------------------------------------------
+    def bp_nwp(self, leaves, ext=None):
+        """leaves [B,n_L], ext f32 [B,q] or None -> next-token posteriors f32 [B,n_L-1,q]  (reference :336-463)."""
+        leaves = leaves.contiguous()
+        B = leaves.shape[0]
+        assert leaves.shape[1] == self.n_leaves and leaves.device == self.device
+        if ext is not None:
+            ext = ext.contiguous()
+            assert ext.dtype == torch.float32 and tuple(ext.shape) == (B, self.q)
+        with torch.cuda.device(self.device):
+            pp = torch.empty((B, self.n_leaves - 1, self.q), dtype=torch.float32, device=self.device)
+            ws = self._workspace(self._lib.ghm_bp_nwp_workspace_bytes(self._h, B))
+            check(self._lib.ghm_bp_nwp(self._h, B, _ptr(leaves), _leaf_code(leaves), _ptr(ext), _ptr(pp), _ptr(ws),
+                                       _stream()))
+        return pp
+
+    # ---- K5 ---------------------------------------------------------------------------
+    @staticmethod
+    def _ptr_array(tensors):
+        arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        return arr
+
+    def guides_cls(self, leaves):
+        """-> (L guide tensors f32 [B,n_L,q] (depth L-1..0), post [B,q], root_hd [B,q])  (reference :533-549)."""
+        leaves = leaves.contiguous()
+        B = leaves.shape[0]
+        with torch.cuda.device(self.device):
+            guides = [torch.empty((B, self.n_leaves, self.q), dtype=torch.float32, device=self.device)
+                      for _ in range(self.L)]
+            post = torch.empty((B, self.q), dtype=torch.float32, device=self.device)
+            hd = torch.empty((B, self.q), dtype=torch.float32, device=self.device)
+            check(self._lib.ghm_guides_cls(self._h, B, _ptr(leaves), _leaf_code(leaves), self._ptr_array(guides),
+                                           _ptr(post), _ptr(hd), _stream()))
+        return guides, post, hd
+
+    def guides_dns(self, z, sigma, ext=None):
+        """-> (2L+1 guide tensors, mean [B,n_L])  (reference :551-590)."""
+        z = z.contiguous()
+        B = z.shape[0]
+        q, nL = self.q, self.n_leaves
+        if ext is not None:
+            ext = ext.contiguous()
+        with torch.cuda.device(self.device):
+            widths = [2 * q] * self.L + [2 * q] + [3 * q] * self.L
+            guides = [torch.empty((B, nL, w), dtype=torch.float32, device=self.device) for w in widths]
+            mean = torch.empty((B, nL), dtype=torch.float32, device=self.device)
+            ws = self._workspace(self._lib.ghm_guides_dns_workspace_bytes(self._h, B))
+            check(self._lib.ghm_guides_dns(self._h, B, _ptr(z), float(sigma), _ptr(ext), self._ptr_array(guides),
+                                           _ptr(mean), _ptr(ws), _stream()))
+        return guides, mean
+
+    def guides_nwp(self, leaves, ext=None):
+        """-> (2L+1 guide tensors [B,n_L-1,{q,2q,...,2q,q,...}], pp [B,n_L-1,q])  (reference :357-459)."""
+        leaves = leaves.contiguous()
+        B = leaves.shape[0]
+        q, nL = self.q, self.n_leaves
+        if ext is not None:
+            ext = ext.contiguous()
+        with torch.cuda.device(self.device):
+            widths = [q] + [2 * q] * self.L + [q] * self.L
+            guides = [torch.empty((B, nL - 1, w), dtype=torch.float32, device=self.device) for w in widths]
+            pp = torch.empty((B, nL - 1, q), dtype=torch.float32, device=self.device)
+            ws = self._workspace(self._lib.ghm_guides_nwp_workspace_bytes(self._h, B))
+            check(self._lib.ghm_guides_nwp(self._h, B, _ptr(leaves), _leaf_code(leaves), _ptr(ext),
+                                           self._ptr_array(guides), _ptr(pp), _ptr(ws), _stream()))
+        return guides, pp
+
     # ---- Gaussian observations ---------------------------------------------------------
     def gauss_noise(self, leaves, sigma, seed=0, tree_offset=0):
         """z = leaves + sigma*N(0,1) (Philox stream 1) -> f32 [B, n_L]."""
@@ -141,6 +229,17 @@ class GhmModel:
 
 
 IMAGE_SEED_XOR = 0x1234567887654321
+
+
+def sample_into(model, batch, root_mode, root_in, seed, tree_offset, root_out, leaves_out, post_out, root_hd_out):
+    """Philox-mode ghm_sample into caller-owned device tensors (views allowed when contiguous): no allocation."""
+    for t in (root_in, root_out, leaves_out, post_out, root_hd_out):
+        assert t is None or t.is_contiguous()
+    with torch.cuda.device(model.device):
+        check(model._lib.ghm_sample(model._h, int(batch), root_mode, _ptr(root_in), C.c_void_p(0), seed, tree_offset,
+                                    _ptr(root_out), _ptr(leaves_out),
+                                    _leaf_code(leaves_out) if leaves_out is not None else LEAF_I64,
+                                    _ptr(post_out), _ptr(root_hd_out), _stream()))
 
 
 def new_sums(device):
