@@ -1,0 +1,141 @@
+"""GPU parity tests for K3 (BP_DNS), K4 (next-token BP) and K5 (guide tensors) through the C ABI.
+
+Checked against the committed reference fixtures (tests/golden/tree_*.npz, generated from the
+real reference) and, on larger seeded batches, against the float64 oracle.  Bars: posterior
+means / next-token posteriors within 1e-5 relative (float32), guide tensors (shifted log
+messages) within 2e-5 absolute + 1e-5 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TREE_CASES, load_tree_case
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ghm_b200 import ops as _ops
+    assert torch.cuda.is_available()
+    return _ops
+
+
+def _model(ops, c):
+    return ops.GhmModel(c["T"], c["L"], c["s"], c["q"], p_y=c["p_y"], device="cuda:0")
+
+
+def _bq(x):     # (q,B) numpy -> device f32 [B,q]
+    return torch.from_numpy(np.ascontiguousarray(x.T)).float().cuda()
+
+
+def _cmp_guides(got, c, tag, n, atol=2e-5):
+    assert len(got) == n
+    for i, g in enumerate(got):
+        ref = c[f"{tag}_guide{i}"]
+        g = g.cpu().numpy()
+        assert g.shape == ref.shape and g.dtype == np.float32, (i, g.shape, ref.shape)
+        fin = np.isfinite(ref) & (ref > -80.0)      # entries below e^-80 underflow in f32 by construction
+        np.testing.assert_allclose(g[fin], ref[fin], rtol=RTOL, atol=atol, err_msg=f"{tag} guide {i}")
+
+
+@pytest.mark.parametrize("name", TREE_CASES)
+@pytest.mark.parametrize("tag", ["dns", "dnsx"])
+def test_bp_dns_vs_reference_fixture(ops, name, tag):
+    c = load_tree_case(name)
+    m = _model(ops, c)
+    z = _bq(c["z"])
+    ext = _bq(c["ext"]) if tag == "dnsx" else None
+    mean = m.bp_dns(z, c["sigma"], ext)
+    np.testing.assert_allclose(mean.cpu().numpy(), c[f"{tag}_mean"].T, rtol=RTOL, atol=2e-6)
+    guides, mean2 = m.guides_dns(z, c["sigma"], ext)       # independent log-domain implementation
+    np.testing.assert_allclose(mean2.cpu().numpy(), c[f"{tag}_mean"].T, rtol=RTOL, atol=2e-6)
+    _cmp_guides(guides, c, tag, 2 * c["L"] + 1)
+
+
+@pytest.mark.parametrize("name", TREE_CASES)
+def test_guides_cls_vs_reference_fixture(ops, name):
+    c = load_tree_case(name)
+    m = _model(ops, c)
+    leaves = torch.from_numpy(np.ascontiguousarray(c[f"val{c['L']}"].T)).cuda()
+    guides, post, hd = m.guides_cls(leaves)
+    np.testing.assert_allclose(post.cpu().numpy(), c["cls_post"].T, rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(hd.cpu().numpy(), c["cls_root_hd"].T, rtol=RTOL, atol=2e-5)
+    _cmp_guides(guides, c, "cls", c["L"])
+    # cross-check the two BP_CLS implementations (linear DFS vs log level-synchronous)
+    p2, h2 = m.bp_cls(leaves)
+    np.testing.assert_allclose(p2.cpu().numpy(), post.cpu().numpy(), rtol=RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", [n for n in TREE_CASES])
+@pytest.mark.parametrize("tag", ["nwp", "nwpx"])
+def test_bp_nwp_vs_reference_fixture(ops, name, tag):
+    c = load_tree_case(name)
+    m = _model(ops, c)
+    leaves = torch.from_numpy(np.ascontiguousarray(c[f"val{c['L']}"].T)).cuda()
+    ext = _bq(c["ext"]) if tag == "nwpx" else None
+    pp = m.bp_nwp(leaves, ext)
+    assert pp.shape == c[f"{tag}_pp"].shape
+    np.testing.assert_allclose(pp.cpu().numpy(), c[f"{tag}_pp"], rtol=RTOL, atol=1e-7)
+    guides, pp2 = m.guides_nwp(leaves.to(torch.uint8), ext)
+    np.testing.assert_allclose(pp2.cpu().numpy(), c[f"{tag}_pp"], rtol=RTOL, atol=1e-7)
+    _cmp_guides(guides, c, tag, 2 * c["L"] + 1)
+
+
+@pytest.mark.parametrize("L,s,q,ti,B,sigma", [(4, 3, 10, True, 2051, 1.0), (3, 4, 10, True, 515, 0.1),
+                                               (6, 2, 7, False, 300, 0.5), (2, 8, 16, True, 200, 2.0),
+                                               (1, 5, 12, True, 65, 0.7), (5, 3, 4, False, 130, 1.0)])
+def test_bp_dns_and_nwp_vs_oracle(ops, L, s, q, ti, B, sigma):
+    from oracle import ghm_oracle as O
+    rng = np.random.RandomState(L * 100 + s * 10 + q)
+    np.random.seed(L * 1000 + s * 10 + q + 1)
+    T = O.gen_transition(L, s, q, 0.2, 1.0, ti)
+    root = rng.randint(0, q, size=B)
+    vals = O.sample_tree(T, L, s, q, B, root=root, U=rng.rand(O.n_edges(L, s), B))
+    leaves = vals[-1]
+    z = leaves + sigma * rng.randn(*leaves.shape)
+    ext = np.log(rng.dirichlet(np.ones(q), size=B).T)
+    ext -= ext.max(0)
+    m = ops.GhmModel(T, L, s, q, device="cuda:0")
+    mean, *_ = O.bp_dns(T, z, sigma, L, s, q, ext=ext)
+    got = m.bp_dns(_bq(z), sigma, _bq(ext))
+    np.testing.assert_allclose(got.cpu().numpy(), mean.T, rtol=RTOL, atol=5e-6)
+    mean0, *_ = O.bp_dns(T, z, sigma, L, s, q)
+    got0 = m.bp_dns(_bq(z), sigma, None)
+    np.testing.assert_allclose(got0.cpu().numpy(), mean0.T, rtol=RTOL, atol=5e-6)
+    if B <= 600:
+        pp, _ = O.bp_nwp(T, leaves, L, s, q, ext=ext)
+        gotp = m.bp_nwp(torch.from_numpy(np.ascontiguousarray(leaves.T)).cuda(), _bq(ext))
+        np.testing.assert_allclose(gotp.cpu().numpy(), pp, rtol=RTOL, atol=1e-7)
+    assert m.status() == 0
+
+
+def test_risk_cdm_and_ce_vs_numpy(ops):
+    rng = np.random.RandomState(1)
+    B, nL, q = 1000, 27, 10
+    mean = rng.rand(B, nL).astype(np.float32) * 9
+    x = rng.randint(0, q, size=(B, nL))
+    loss = np.sum((mean.astype(np.float64) - x) ** 2, 1)
+    sums = ops.risk_cdm(torch.from_numpy(mean).cuda(), torch.from_numpy(x).cuda())
+    m, se = ops.mean_se(sums)
+    assert m == pytest.approx(loss.mean(), rel=1e-12) and se == pytest.approx(loss.std() / np.sqrt(B), rel=1e-9)
+    pp = rng.dirichlet(np.ones(q), size=(B, nL - 1)).astype(np.float32)
+    ce = -np.log(pp[np.arange(B)[:, None], np.arange(nL - 1)[None, :], x[:, 1:]])
+    sums = ops.risk_ce(torch.from_numpy(pp).cuda(), torch.from_numpy(x).cuda(), target_stride=nL, target_offset=1,
+                       row_group=nL - 1)
+    assert ops.mean_se(sums)[0] == pytest.approx(ce.astype(np.float64).mean(), rel=1e-6)
+
+
+def test_gauss_noise_matches_philox_oracle_and_is_normal(ops):
+    from oracle import ghm_oracle as O, philox
+    np.random.seed(1)
+    L, s, q, B = 3, 3, 10, 4096
+    T = O.gen_transition(L, s, q, 0.2, 1.0, True)
+    m = ops.GhmModel(T, L, s, q, device="cuda:0")
+    out = m.sample(B, seed=3, root_mode=ops.ROOT_UNIFORM)
+    z = m.gauss_noise(out["leaves"], 0.5, seed=77, tree_offset=10)
+    g = (z - out["leaves"].float()).cpu().numpy() / 0.5
+    ref = philox.gauss_noise(77, 10, B, s ** L).T
+    np.testing.assert_allclose(g, ref, rtol=0, atol=2e-5)
+    assert abs(g.mean()) < 5 / np.sqrt(g.size) and abs(g.std() - 1) < 0.01

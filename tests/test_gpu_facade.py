@@ -112,3 +112,133 @@ def test_philox_clip_bayes_statistical_and_sharded(G, kat):
         rr = s2._sample_layout(n, want_leaves=False, want_post=True, pair_lo=lo, pair_hi=hi)
         ops.risk_clip(rr["t"]["post"], rr["i"]["post"], hi - lo, 4, 10, sums=tot)
     assert mean_se_from_sums(tot)[0] == pytest.approx(float(whole), rel=1e-12)
+
+
+def test_kat_cdm_bayes(G, kat):
+    """cdm-risk.json Bayes[0,9]: ConditionalDenoiseSampler(...).get_Bayes(10000), sigma=1 (reference train_CDNS.py:66-75)."""
+    for idx in (0, 9):
+        p = 0.02 * (idx + 1)
+        s = G.ConditionalDenoiseSampler([4, 4], [3, 3], [u10, u10], [p, p])
+        val, se = s.get_Bayes(n_eval=10000)
+        assert val == pytest.approx(kat["cdm-risk.json"]["Bayes"][idx], rel=1e-5)
+
+
+def test_kat_vlm_bayes(G, kat):
+    """vlm-risk.json Bayes[0]: NextWordPredictSampler(...).get_Bayes(10000) (reference train_NWP.py:65-74)."""
+    s = G.NextWordPredictSampler([4, 4], [3, 3], [u10, u10], [.02, .02])
+    val, se = s.get_Bayes(n_eval=10000)
+    assert isinstance(val, torch.Tensor) and val.dtype == torch.float32
+    assert val.item() == pytest.approx(kat["vlm-risk.json"]["Bayes"][0], rel=1e-5)
+
+
+def test_mis_specified_vlm_bp_recipe(G, kat):
+    """vlm-ood.json Mis-spec. BP[0]: BP-only part of figures/eval-vlm-ood.py:98-132 (B=1000), with the
+    caller-side item assignment into T_value[-1] (:117)."""
+    B = 1000
+    ts = G.DoubleSampler([4, 4], [3, 3], [u10, u10], [.2, .2])
+    text_tree, image_tree = ts.get_zeroshot_batch(batch_size=B, return_tree=True)
+    s = G.NextWordPredictSampler([4, 4], [3, 3], [u10, u10], [.02, .02])
+    s.get_Bayes(n_eval=10000)
+    res_text, res_image = s.get_batch(device="cpu", batch_size=B, guide=False)
+    for idx in range(80):
+        text_tree.T_value[-1][idx] = res_text[0][:, idx].tolist()
+    image_tree.T_value[-1] = [res_image[0][:, idx].tolist() for idx in range(81)]
+    text_tree.build_tree()
+    image_tree.build_tree()
+    image_tree.BP_CLS()
+    ext = image_tree.root_node.hd_message
+    assert ext.shape == (10, B)
+    out, _ = text_tree.BP_NWP_autoregressive(external_hd_message=ext, device="cpu", guide_info=False)
+    pred = out.reshape(-1, 10)
+    target = res_text[1].reshape(-1)
+    loss = torch.mean(-torch.log(pred[range(len(target)), target])).item()
+    assert loss == pytest.approx(kat["vlm-ood.json"]["Mis-spec. BP"][0], rel=1e-5)
+
+
+def test_get_batch_structures_vs_reference_fixture(G, gold):
+    """Return structure, shapes, dtypes and values of every sampler's get_batch."""
+    def cmp_guides(got, prefix, atol=2e-5):
+        n = len([k for k in gold if k.startswith(prefix)])
+        assert len(got) == n
+        for i, g in enumerate(got):
+            ref = gold[f"{prefix}{i}"]
+            assert g.dtype == torch.float32 and tuple(g.shape) == ref.shape
+            fin = np.isfinite(ref) & (ref > -80)
+            np.testing.assert_allclose(g.cpu().numpy()[fin], ref[fin], rtol=1e-5, atol=atol)
+
+    s = G.ClipSampler([2, 3], [2, 2], [u10, u10], [.2, .3], K=4)
+    rt, ri = s.get_batch(batch_size=6, guide=True)
+    assert np.array_equal(rt[0].numpy(), gold["clip_t_leaves"]) and np.array_equal(ri[1].numpy(), gold["clip_i_root"])
+    assert rt[3].dtype == np.float64 and rt[3].shape == gold["clip_t_pp"].shape
+    np.testing.assert_allclose(rt[3], gold["clip_t_pp"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(ri[3], gold["clip_i_pp"], rtol=1e-5, atol=1e-7)
+    cmp_guides(rt[2], "clip_t_guide")
+    cmp_guides(ri[2], "clip_i_guide")
+
+    s = G.ConditionalDenoiseSampler([2, 3], [3, 2], [u10, u10], [.2, .1], sigma=0.7)
+    rt, ri = s.get_batch(batch_size=9, guide=True)
+    assert np.array_equal(rt[0].numpy(), gold["cdm_t_leaves"]) and np.array_equal(rt[1].numpy(), gold["cdm_t_root"])
+    assert rt[3].shape == gold["cdm_t_pp"].shape            # (q, B): untransposed in the reference (:884)
+    np.testing.assert_allclose(rt[3], gold["cdm_t_pp"], rtol=1e-5, atol=1e-7)
+    assert ri[0].dtype == torch.float32 and ri[1].dtype == torch.int64
+    np.testing.assert_allclose(ri[0].numpy(), gold["cdm_z"], rtol=1e-6)
+    assert np.array_equal(ri[1].numpy(), gold["cdm_i_leaves"])
+    assert ri[3].dtype == np.float64
+    np.testing.assert_allclose(ri[3], gold["cdm_mean"], rtol=1e-5, atol=2e-6)
+    cmp_guides(rt[2], "cdm_t_guide")
+    cmp_guides(ri[2], "cdm_i_guide")
+    s = G.ConditionalDenoiseSampler([2, 3], [3, 2], [u10, u10], [.2, .1], sigma=0.7)
+    np.testing.assert_allclose(s.get_Bayes(n_eval=64), gold["cdm_bayes_n64"], rtol=1e-5)
+
+    s = G.NextWordPredictSampler([3, 2], [2, 3], [u10, u10], [.15, .25])
+    rt, ri = s.get_batch(batch_size=5, guide=True)
+    assert np.array_equal(rt[0].numpy(), gold["nwp_in"]) and np.array_equal(rt[1].numpy(), gold["nwp_tgt"])
+    assert rt[3].dtype == torch.float32
+    np.testing.assert_allclose(rt[3].numpy(), gold["nwp_pp"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(ri[3], gold["nwp_i_pp"], rtol=1e-5, atol=1e-7)
+    cmp_guides(rt[2], "nwp_t_guide")
+    cmp_guides(ri[2], "nwp_i_guide")
+    s = G.NextWordPredictSampler([3, 2], [2, 3], [u10, u10], [.15, .25])
+    b = s.get_Bayes(n_eval=40)
+    np.testing.assert_allclose([b[0].item(), b[1].item()], gold["nwp_bayes_n40"], rtol=2e-5)
+
+    py = gold["cls_py"]
+    s = G.ClassificationSampler(3, 2, py, p_flip=.25)
+    r = s.get_batch(batch_size=8, guide=True)
+    assert np.array_equal(r[0].numpy(), gold["cls_leaves"]) and np.array_equal(r[1].numpy(), gold["cls_root"])
+    np.testing.assert_allclose(r[3], gold["cls_pp"], rtol=1e-5, atol=1e-7)
+    cmp_guides(r[2], "cls_guide")
+    with pytest.raises(AttributeError):
+        G.ClassificationSampler(3, 2, py, p_flip=.25).get_batch(batch_size=4, guide=False)
+    s = G.ClassificationSampler(3, 2, py, p_flip=.25)
+    np.testing.assert_allclose(s.get_Bayes(n_eval=80), gold["cls_bayes_n80"], rtol=2e-5)
+
+    s = G.DenoiseSampler(2, 3, py, p_flip=.2, sigma=0.5)
+    r = s.get_batch(batch_size=8, guide=True)
+    np.testing.assert_allclose(r[0].numpy(), gold["dns_z"], rtol=1e-6)
+    np.testing.assert_allclose(r[1].numpy(), gold["dns_x"])
+    np.testing.assert_allclose(r[3], gold["dns_mean"], rtol=1e-5, atol=2e-6)
+    cmp_guides(r[2], "dns_guide")
+
+    s = G.DoubleSampler([2, 2], [2, 3], [u10, u10], [.2, .2])
+    tl, il, tpp, ipp, root = s.get_zeroshot_batch(batch_size=7)
+    assert np.array_equal(tl, gold["zs_t_leaves"]) and np.array_equal(il, gold["zs_i_leaves"])
+    assert np.array_equal(root, gold["zs_root"])
+    np.testing.assert_allclose(tpp, gold["zs_t_pp"], rtol=1e-5, atol=1e-7)
+
+
+def test_reference_unit_tests_run_against_facade(G):
+    """The reference's own tests (tests/test_data_randomghm.py:24-54), restated verbatim on the facade:
+    |E[m^2] - E[m x]| < 3e-3 for the conditional and the unconditional denoiser, B = 10000, sigma = 0.1."""
+    def denoise_test(true_leave_values, pred_leave_values):
+        true_leave_values = np.array(true_leave_values)
+        mean_power_res = np.mean(np.power(pred_leave_values, 2), 1)
+        mean_pred_true_res = np.mean(np.multiply(pred_leave_values, true_leave_values), 1)
+        return np.abs(np.mean(mean_power_res) - np.mean(mean_pred_true_res))
+    sampler = G.ConditionalDenoiseSampler([3, 4], [3, 3], [u10, u10], [0.1, 0.1], flip_scale=1, sigma=0.1,
+                                          translation_invariance=True, variable_type=10)
+    _, res_image = sampler.get_batch(batch_size=10000, guide=True)
+    assert denoise_test(res_image[1], res_image[-1]) < 3e-3
+    sampler = G.DenoiseSampler(3, 3, u10, 0.1, flip_scale=1, sigma=0.1, translation_invariance=True, variable_type=10)
+    res = sampler.get_batch(batch_size=10000, guide=True)
+    assert denoise_test(res[1], res[-1]) < 3e-3
