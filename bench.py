@@ -211,15 +211,12 @@ def run_ours(args, rank, world, local_rank):
     def step(seed, record=False):
         """sample text / image (+ fused BP, leaves materialised), contrastive reduction, all-reduce of the sums."""
         sums.zero_()
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if record else None
         if record: evs[0].record()
         ops.sample_into(tm, B, ops.ROOT_UNIFORM, None, seed, tree_off, t_root, t_leaves, t_pp, None)
         if record: evs[1].record()
-        ops.sample_into(im, 2 * n, ops.ROOT_GIVEN, t_root, seed ^ ops.IMAGE_SEED_XOR, tree_off, None, i_leaves, i_pp, None)
+        ops.sample_mixed_into(im, B, 2 * n, t_root, seed ^ ops.IMAGE_SEED_XOR, tree_off, None, i_leaves, i_pp, None)
         if record: evs[2].record()
-        ops.sample_into(im, (K - 1) * n, ops.ROOT_UNIFORM, None, seed ^ ops.IMAGE_SEED_XOR, tree_off + 2 * n, None,
-                        i_leaves[2 * n:], i_pp[2 * n:], None)
-        if record: evs[3].record()
         ops.risk_clip(t_pp, i_pp, n, K, Q, sums=sums)
         if world > 1:
             dist.all_reduce(sums)
@@ -261,18 +258,22 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel (fused sampler + BP), from the per-launch events ------
     launch_ms, launch_bytes = [], []
     for evs in kern_events:
-        for j, (nb, nl, has_root) in enumerate(((B, nLt, True), (2 * n, nLi, True), ((K - 1) * n, nLi, False))):
+        for j, (nb, nl, has_root) in enumerate(((B, nLt, True), (B, nLi, False))):
             launch_ms.append(evs[j].elapsed_time(evs[j + 1]))
             launch_bytes.append(nb * (8 * nl + 4 * Q + (8 if has_root else 0)))
     peak, peak_kind = read_peaks()
     achieved = sum(launch_bytes) / (sum(launch_ms) * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_tree<Q=10,PHILOX,BP> (fused sampler + root-posterior BP, int64 leaves out)",
+    roofline = {"bound": "hbm", "kernel": "k_tree2<Q=10,S=3,TPT=2,PHILOX,BP> (fused sampler + root-posterior BP, int64 leaves out)",
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak,
+                # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r01f_ncu_full_k_tree2.csv:
+                # 171.37 MB written + 0.08 MB read for a 327 680-tree launch = 523.2 B/tree; below the 696 B/tree
+                # algorithmic figure because part of the last leaves is still in the 126 MB L2 when the kernel ends)
+                "traffic": 523.2 * B, "traffic_source": "profiles/r01f_ncu_full_k_tree2.csv",
                 "bytes_per_tree": 8 * nLt + 4 * Q + 8, "avg_launch_ms": sum(launch_ms) / len(launch_ms),
                 "kernel_share_of_step": sum(launch_ms) / ms,
-                "note": "kernel is FP32-issue bound by design (about 11k thread-instructions per tree); "
-                        "HBM fraction is reported, not padded"}
+                "note": "issue-slot / FP32-pipe bound by design (about 10k thread-instructions per tree: Philox 1.2k, "
+                        "alias draws 1k, BP 2.6k FFMA2/FMUL2 + their LDCU/LDS operands); the HBM fraction is reported, not padded"}
 
     # ---- end to end through the reference-facing facade call (host in / host out) --------------
     e2e = e2e_b = None
@@ -336,7 +337,7 @@ def run_ours(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": value, "unit": "trees/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(n, world),
-                "clocks": clk, "e2e": e2e, "e2e_get_batch": e2e_b, "gpu_launches": 4 * args.steps,
+                "clocks": clk, "e2e": e2e, "e2e_get_batch": e2e_b, "gpu_launches": 3 * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu,
                 "bayes_clip_risk": {"mean": risk_mean, "se": risk_se}}
         print(json.dumps(line), flush=True)

@@ -66,7 +66,7 @@ GHM_API int ghm_device_count(void);
  *            per-edge (ti=0):              n_mat = E,   m = BFS edge index
  *   p_y    : [q] root prior (NULL -> uniform)
  * The library derives and uploads: f32 T, f32 T^T, f32 log T^T, f64 CDF (sequential
- * cumsum, bit-identical to np.cumsum, :165) and u32 CDF thresholds (Philox mode). */
+ * cumsum, bit-identical to np.cumsum, :165) and Walker alias tables (Philox mode, O(1) draws). */
 GHM_API int ghm_model_create(ghm_model_t** out, int n_layer, int n_child, int q, int ti,
                      const double* T_host, const double* p_y_host, int device);
 GHM_API int ghm_model_destroy(ghm_model_t* m);
@@ -89,6 +89,12 @@ GHM_API int ghm_sample(const ghm_model_t* m, int64_t B, int root_mode, const int
                const double* U, uint64_t seed, uint64_t tree_offset,
                int64_t* root_out, void* leaves_out, int leaf_dtype,
                float* post_out, float* root_hd_out, void* stream);
+
+/* ClipSampler's image-side root layout in ONE launch (:759-760, `np.append(text_root[:2n], choice(q, n(K-1)))`):
+ * trees [0, n_given) take root_in[b], trees [n_given, B) draw uniform roots.  Philox mode only. */
+GHM_API int ghm_sample_mixed(const ghm_model_t* m, int64_t B, int64_t n_given, const int64_t* root_in,
+                     uint64_t seed, uint64_t tree_offset, int64_t* root_out, void* leaves_out, int leaf_dtype,
+                     float* post_out, float* root_hd_out, void* stream);
 
 /* ---- K2: root posterior  (GHMTree.BP_CLS, :185-221) ----------------------------
  *   post     : f32 [B, q]  p(root | leaves)               (posterior_probability_CLS^T)

@@ -18,11 +18,15 @@
 //   Tlin  [m][a][b]   f32  P(child=b | parent=a)              (up / down matvecs)
 //   TlinT [m][b][a]   f32  same, transposed                   (leaf column gather, linear)
 //   TlogT [m][b][a]   f32  natural log of the above           (leaf column gather, log domain)
-//   cdfu  [m][a][k]   u32  floor(cumsum_k T[a][:] * 2^32), padded with 0xFFFFFFFF   (Philox mode)
+//   TTp   [m][b][a]   f32  TlinT with the row stride padded to QS = roundup(QP, 4) floats, so every
+//                          row starts 16-byte aligned (LDS.128 / packed f32x2 operands)
+//   alias [m][a][k]   u32  Walker alias table of row T[a][:], entry = (thr24 << 8) | alias8, stride q:
+//                          draw u32 r -> m = r*q; k = m >> 32; frac = (u32)m; child = frac < e ? k : e & 255
+//                          (Philox mode: O(1) per draw; oracle/philox.py builds the identical table)
 //   cdfd  [m][a][k]   f64  sequential cumsum, unpadded stride q                     (parity mode)
 // ------------------------------------------------------------------------------------
 struct GhmDev {
-    int L, s, q, QP, ti;
+    int L, s, q, QP, QS, ti;
     int n_mat;
     int n_leaves;                          // s^L
     int n_edges;                           // sum_{l=1..L} s^l
@@ -34,7 +38,8 @@ struct GhmDev {
     const float* Tlin;
     const float* TlinT;
     const float* TlogT;
-    const uint32_t* cdfu;
+    const float* TTp;
+    const uint32_t* alias;
     const double* cdfd;
     const float* py;                       // [QP] prior, zero padded
     const uint32_t* root_cdfu_prior;       // [QP]
@@ -45,6 +50,7 @@ struct GhmDev {
 struct ghm_model {
     GhmDev d;
     int device;
+    float* h_TTp;        // host copy of TTp (source of the constant-bank kernel parameter)
     void* slab;          // single device allocation holding every table
     size_t slab_bytes;
     cudaStream_t stream; // internal stream for ghm_host_* entry points

@@ -63,15 +63,8 @@ extern "C" int ghm_host_clip_bayes(const ghm_model_t* text_c, const ghm_model_t*
     if (rc) return rc;
     // image: first 2n trees share the text roots, the other (K-1)n draw fresh uniform roots (:759-760)
     const uint64_t iseed = seed ^ GHM_IMAGE_SEED_XOR;
-    rc = ghm_sample(image, 2 * n, GHM_ROOT_GIVEN, d_root, nullptr, iseed, tree_offset, nullptr, d_il, leaf_dtype, d_ipp,
-                    nullptr, st);
+    rc = ghm_sample_mixed(image, B, 2 * n, d_root, iseed, tree_offset, nullptr, d_il, leaf_dtype, d_ipp, nullptr, st);
     if (rc) return rc;
-    if (K > 1) {
-        void* il2 = d_il ? (void*)((char*)d_il + (size_t)2 * n * image->d.n_leaves * lsz) : nullptr;
-        rc = ghm_sample(image, (K - 1) * n, GHM_ROOT_UNIFORM, nullptr, nullptr, iseed, tree_offset + 2 * (uint64_t)n,
-                        nullptr, il2, leaf_dtype, d_ipp + (size_t)2 * n * q, nullptr, st);
-        if (rc) return rc;
-    }
     rc = ghm_risk_clip(d_tpp, d_ipp, n, K, q, 0, n, d_sums, st);
     if (rc) return rc;
     GHM_CUDA_TRY(cudaMemcpyAsync(sums_host, d_sums, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));

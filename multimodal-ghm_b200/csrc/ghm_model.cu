@@ -5,6 +5,7 @@
 // transition matrices (GenTransition, :43-89) and this file derives every device table.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -55,7 +56,8 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     GhmDev& d = m->d;
     d.L = L; d.s = s; d.q = q; d.ti = ti ? 1 : 0;
     d.QP = ghm_pad_q(q) ? ghm_pad_q(q) : (int)align_up(q, 4);
-    const int QP = d.QP;
+    d.QS = (int)align_up(d.QP, 4);
+    const int QP = d.QP, QS = d.QS;
     d.spow[0] = 1;
     for (int l = 1; l <= L; ++l) d.spow[l] = d.spow[l - 1] * s;
     for (int l = L + 1; l <= GHM_MAX_LEVELS; ++l) d.spow[l] = 0;
@@ -77,8 +79,11 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     // ---- derive the host tables ---------------------------------------------------
     const size_t nm = (size_t)d.n_mat, QQ = (size_t)QP * QP;
     std::vector<float> Tlin(nm * QQ, 0.f), TlinT(nm * QQ, 0.f), TlogT(nm * QQ, -INFINITY);
-    std::vector<uint32_t> cdfu(nm * QQ, 0xFFFFFFFFu);
+    std::vector<float> TTp(nm * (size_t)QP * QS, 0.f);
+    std::vector<uint32_t> alias(nm * (size_t)q * q, 0u);
     std::vector<double> cdfd(nm * (size_t)q * q, 0.0);
+    std::vector<double> scaled(q);
+    std::vector<int> small, large;
     for (size_t mi = 0; mi < nm; ++mi) {
         const double* T = T_host + mi * (size_t)q * q;
         for (int a = 0; a < q; ++a) {
@@ -92,10 +97,28 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
                 Tlin[mi * QQ + (size_t)a * QP + b] = (float)t;
                 TlinT[mi * QQ + (size_t)b * QP + a] = (float)t;
                 TlogT[mi * QQ + (size_t)b * QP + a] = (float)log(t);
+                TTp[mi * (size_t)QP * QS + (size_t)b * QS + a] = (float)t;
                 run = (b == 0) ? t : run + t;                 // np.cumsum: sequential f64 adds
                 cdfd[mi * (size_t)q * q + (size_t)a * q + b] = run;
-                double thr = floor(run * 4294967296.0);
-                cdfu[mi * QQ + (size_t)a * QP + b] = thr >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr;
+            }
+            // Walker/Vose alias table of row a (oracle/philox.py::alias_table performs the same f64 steps in
+            // the same order, so Philox-mode samples are reproducible bit-for-bit on the CPU)
+            small.clear(); large.clear();
+            for (int b = 0; b < q; ++b) {
+                scaled[b] = T[(size_t)a * q + b] * (double)q;
+                (scaled[b] < 1.0 ? small : large).push_back(b);
+            }
+            uint32_t* arow = &alias[mi * (size_t)q * q + (size_t)a * q];
+            for (int b = 0; b < q; ++b) arow[b] = 0xFFFFFF00u | (uint32_t)b;        // prob 1, alias = self
+            while (!small.empty() && !large.empty()) {
+                const int sm = small.back(); small.pop_back();
+                const int lg = large.back(); large.pop_back();
+                double thr = floor(scaled[sm] * 16777216.0);
+                if (thr < 0.0) thr = 0.0;
+                if (thr > 16777215.0) thr = 16777215.0;
+                arow[sm] = ((uint32_t)thr << 8) | (uint32_t)lg;
+                scaled[lg] = (scaled[lg] + scaled[sm]) - 1.0;
+                (scaled[lg] < 1.0 ? small : large).push_back(lg);
             }
         }
     }
@@ -118,7 +141,7 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     size_t o_Tlin = take(Tlin.size() * 4), o_TlinT = take(TlinT.size() * 4), o_TlogT = take(TlogT.size() * 4);
-    size_t o_cdfu = take(cdfu.size() * 4), o_cdfd = take(cdfd.size() * 8);
+    size_t o_TTp = take(TTp.size() * 4), o_alias = take(alias.size() * 4), o_cdfd = take(cdfd.size() * 8);
     size_t o_py = take(py.size() * 4), o_rcp = take(rc_prior.size() * 4), o_rcu = take(rc_unif.size() * 4);
     size_t o_status = take(sizeof(int));
     m->slab_bytes = off;
@@ -149,7 +172,8 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     MC_TRY(cudaMemcpy(base + o_Tlin, Tlin.data(), Tlin.size() * 4, cudaMemcpyHostToDevice));
     MC_TRY(cudaMemcpy(base + o_TlinT, TlinT.data(), TlinT.size() * 4, cudaMemcpyHostToDevice));
     MC_TRY(cudaMemcpy(base + o_TlogT, TlogT.data(), TlogT.size() * 4, cudaMemcpyHostToDevice));
-    MC_TRY(cudaMemcpy(base + o_cdfu, cdfu.data(), cdfu.size() * 4, cudaMemcpyHostToDevice));
+    MC_TRY(cudaMemcpy(base + o_TTp, TTp.data(), TTp.size() * 4, cudaMemcpyHostToDevice));
+    MC_TRY(cudaMemcpy(base + o_alias, alias.data(), alias.size() * 4, cudaMemcpyHostToDevice));
     MC_TRY(cudaMemcpy(base + o_cdfd, cdfd.data(), cdfd.size() * 8, cudaMemcpyHostToDevice));
     MC_TRY(cudaMemcpy(base + o_py, py.data(), py.size() * 4, cudaMemcpyHostToDevice));
     MC_TRY(cudaMemcpy(base + o_rcp, rc_prior.data(), rc_prior.size() * 4, cudaMemcpyHostToDevice));
@@ -161,7 +185,10 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     d.Tlin = (const float*)(base + o_Tlin);
     d.TlinT = (const float*)(base + o_TlinT);
     d.TlogT = (const float*)(base + o_TlogT);
-    d.cdfu = (const uint32_t*)(base + o_cdfu);
+    m->h_TTp = (float*)malloc(TTp.size() * sizeof(float));
+    if (m->h_TTp) memcpy(m->h_TTp, TTp.data(), TTp.size() * sizeof(float));
+    d.TTp = (const float*)(base + o_TTp);
+    d.alias = (const uint32_t*)(base + o_alias);
     d.cdfd = (const double*)(base + o_cdfd);
     d.py = (const float*)(base + o_py);
     d.root_cdfu_prior = (const uint32_t*)(base + o_rcp);
@@ -180,6 +207,7 @@ extern "C" int ghm_model_destroy(ghm_model_t* m) {
     if (m->slab) cudaFree(m->slab);
     if (m->d_scratch) cudaFree(m->d_scratch);
     if (m->h_scratch) cudaFreeHost(m->h_scratch);
+    free(m->h_TTp);
     cudaSetDevice(prev);
     delete m;
     return GHM_OK;

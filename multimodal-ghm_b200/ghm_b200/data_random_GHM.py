@@ -576,7 +576,7 @@ class ClipSampler(DoubleSampler):
         nl = pair_hi - pair_lo
         off = self._advance(B)
         dev = self.device
-        if nl == n:      # whole layout on this device: 3 launches over contiguous global tree ranges
+        if nl == n:      # whole layout on this device: one launch per modality over contiguous global tree ranges
             t = {"leaves": torch.empty((B, self.t_model.n_leaves), dtype=torch.int64, device=dev) if want_leaves else None,
                  "root": torch.empty(B, dtype=torch.int64, device=dev),
                  "post": torch.empty((B, q), dtype=torch.float32, device=dev) if want_post else None}
@@ -584,12 +584,8 @@ class ClipSampler(DoubleSampler):
                  "root": torch.empty(B, dtype=torch.int64, device=dev),
                  "post": torch.empty((B, q), dtype=torch.float32, device=dev) if want_post else None}
             iseed = self.seed ^ ops.IMAGE_SEED_XOR
-            cut = lambda x, a, b: None if x is None else x[a:b]
             ops.sample_into(self.t_model, B, ops.ROOT_UNIFORM, None, self.seed, off, t["root"], t["leaves"], t["post"], None)
-            ops.sample_into(self.i_model, 2 * n, ops.ROOT_GIVEN, t["root"][:2 * n], iseed, off, cut(i["root"], 0, 2 * n),
-                            cut(i["leaves"], 0, 2 * n), cut(i["post"], 0, 2 * n), None)
-            ops.sample_into(self.i_model, (K - 1) * n, ops.ROOT_UNIFORM, None, iseed, off + 2 * n, cut(i["root"], 2 * n, B),
-                            cut(i["leaves"], 2 * n, B), cut(i["post"], 2 * n, B), None)
+            ops.sample_mixed_into(self.i_model, B, 2 * n, t["root"], iseed, off, i["root"], i["leaves"], i["post"], None)
             return {"t": t, "i": i, "n_local": n}
         Bl = nl * (K + 1)
         t = {"leaves": torch.empty((Bl, self.t_model.n_leaves), dtype=torch.int64, device=dev) if want_leaves else None,

@@ -242,6 +242,17 @@ def sample_into(model, batch, root_mode, root_in, seed, tree_offset, root_out, l
                                     _ptr(post_out), _ptr(root_hd_out), _stream()))
 
 
+def sample_mixed_into(model, batch, n_given, root_in, seed, tree_offset, root_out, leaves_out, post_out, root_hd_out):
+    """ghm_sample_mixed: trees [0, n_given) take ``root_in``, the rest draw uniform roots (ClipSampler image layout)."""
+    for t in (root_in, root_out, leaves_out, post_out, root_hd_out):
+        assert t is None or t.is_contiguous()
+    with torch.cuda.device(model.device):
+        check(model._lib.ghm_sample_mixed(model._h, int(batch), int(n_given), _ptr(root_in), seed, tree_offset,
+                                          _ptr(root_out), _ptr(leaves_out),
+                                          _leaf_code(leaves_out) if leaves_out is not None else LEAF_I64,
+                                          _ptr(post_out), _ptr(root_hd_out), _stream()))
+
+
 def new_sums(device):
     """Zeroed {sum, sum of squares, count} accumulator (float64[3]) for the risk kernels."""
     return torch.zeros(3, dtype=torch.float64, device=device)

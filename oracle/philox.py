@@ -3,8 +3,10 @@
 The reference has no counter-based RNG (it uses NumPy's global MT19937 stream);
 Philox mode is this repo's device-side RNG, so there is no reference code to cite.
 This file restates ``philox4x32_10`` / ``ghm_rng_block`` of
-``multimodal-ghm_b200/csrc/ghm_common.cuh`` and the integer-threshold inverse CDF
-of ``csrc/ghm_vec.cuh`` so that Philox-mode samples can be checked bit-for-bit.
+``multimodal-ghm_b200/csrc/ghm_common.cuh``, the Walker alias tables built by
+``ghm_model_create`` (``csrc/ghm_model.cu``) and the alias draw of ``csrc/ghm_vec2.cuh``
+(root draws keep the integer-threshold inverse CDF) so that Philox-mode samples can be
+checked bit-for-bit.
 Philox4x32-10 itself is pinned to the Random123 known-answer vectors in
 ``tests/test_oracle_philox.py``.
 """
@@ -54,9 +56,57 @@ def search(thr_rows, r, q):
     return (np.asarray(r, dtype=np.uint64)[:, None] >= thr_rows[:, :q - 1]).sum(axis=1).astype(np.int64)
 
 
+def alias_table(row_probs):
+    """Walker/Vose alias table of one probability row -> uint64 [q] entries (thr24 << 8) | alias8.
+
+    Same float64 operations in the same order as ``ghm_model_create`` (csrc/ghm_model.cu): small /
+    large work-lists in ascending index order, popped from the back.
+    """
+    p = np.asarray(row_probs, dtype=np.float64)
+    q = p.shape[0]
+    scaled = [float(p[b]) * float(q) for b in range(q)]
+    small = [b for b in range(q) if scaled[b] < 1.0]
+    large = [b for b in range(q) if not scaled[b] < 1.0]
+    entry = [0xFFFFFF00 | b for b in range(q)]
+    while small and large:
+        sm = small.pop()
+        lg = large.pop()
+        thr = float(np.floor(scaled[sm] * 16777216.0))
+        thr = min(max(thr, 0.0), 16777215.0)
+        entry[sm] = (int(thr) << 8) | lg
+        scaled[lg] = (scaled[lg] + scaled[sm]) - 1.0
+        (small if scaled[lg] < 1.0 else large).append(lg)
+    return np.array(entry, dtype=np.uint64)
+
+
+def draw_alias(entries, r, q):
+    """child = frac < e ? k : e & 255 with m = r*q, k = m >> 32, frac = m mod 2^32; entries [B, q], r [B]."""
+    m = np.asarray(r, dtype=np.uint64) * np.uint64(q)
+    k = (m >> np.uint64(32)).astype(np.int64)
+    frac = m & MASK
+    e = entries[np.arange(entries.shape[0]), k]
+    return np.where(frac < e, k, (e & np.uint64(255)).astype(np.int64)).astype(np.int64)
+
+
+def draw_words_at(seed, trees, level, blocks, words, stream=0):
+    """uint32 [n, B]: word ``words[i]`` of Philox block ``blocks[i]`` of ``level`` for every tree."""
+    trees = np.asarray(trees, dtype=np.uint64)
+    blocks = np.asarray(blocks, dtype=np.uint64)
+    w = philox4x32_10(trees[None, :] & MASK, trees[None, :] >> np.uint64(32), blocks[:, None],
+                      np.uint64(level | (stream << 8)), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    stack = np.stack(np.broadcast_arrays(*w), axis=0)            # [4, n, B]
+    return stack[np.asarray(words, dtype=np.int64), np.arange(len(blocks)), :]
+
+
 def sample_tree_philox(transition, n_layer, n_child, q, batch, seed, tree_offset=0, root=None, p_y=None,
                        root_uniform=False):
-    """Philox-mode twin of oracle.ghm_oracle.sample_tree: same traversal, Philox words instead of U."""
+    """Philox-mode twin of oracle.ghm_oracle.sample_tree: same traversal, Philox words instead of U.
+
+    Counter layout (csrc/ghm_tree.cu): root = word 0 of block (level 0, 0); the s leaves under
+    depth-(L-1) node j take words c % 4 of blocks (level L, j*ceil(s/4) + c // 4); when s % 4 != 0 and
+    L >= 2 node j itself is drawn from the spare word s % 4 of its last leaf block; every other node
+    (l, idx) uses word idx & 3 of block (level l, idx >> 2).
+    """
     trees = np.arange(batch, dtype=np.uint64) + np.uint64(tree_offset)
     if root is None:
         p = np.full(q, 1.0 / q) if (root_uniform or p_y is None) else np.asarray(p_y, dtype=np.float64)
@@ -64,15 +114,28 @@ def sample_tree_philox(transition, n_layer, n_child, q, batch, seed, tree_offset
         root = search(np.broadcast_to(thresholds(p), (batch, q)), r, q)
     root = np.asarray(root, dtype=np.int64)
     values = [root.reshape(1, batch)]
-    s = n_child
-    for layer in range(1, n_layer + 1):
+    s, L = n_child, n_layer
+    nb = (s + 3) // 4
+    spare = (s % 4 != 0) and L >= 2
+    for layer in range(1, L + 1):
         prev = values[-1]
         n = s ** layer
-        words = draw_words(seed, trees, layer, n)
+        idx = np.arange(n)
+        if layer == L:
+            j, c = idx // s, idx % s
+            words = draw_words_at(seed, trees, L, j * nb + c // 4, c % 4)
+        elif layer == L - 1 and spare:
+            words = draw_words_at(seed, trees, L, idx * nb + nb - 1, np.full(n, s % 4))
+        else:
+            words = draw_words_at(seed, trees, layer, idx >> 2, idx & 3)
         cur = np.empty((n, batch), dtype=np.int64)
-        for idx in range(n):
-            thr = thresholds(transition[layer - 1][idx])        # [q, q]
-            cur[idx] = search(thr[prev[idx // s]], words[idx], q)
+        cache = {}
+        for i in range(n):
+            mat = transition[layer - 1][i]
+            key = id(mat)
+            if key not in cache:
+                cache[key] = np.stack([alias_table(mat[a]) for a in range(q)])      # [q parent, q]
+            cur[i] = draw_alias(cache[key][prev[i // s]], words[i], q)
         values.append(cur)
     return values
 

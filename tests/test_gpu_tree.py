@@ -74,7 +74,9 @@ def test_sampling_and_bp_vs_oracle(ops, L, s, q, ti, B):
     assert m.status() == 0
 
 
-@pytest.mark.parametrize("L,s,q,ti,B", [(4, 3, 10, True, 1031), (3, 2, 5, False, 200), (2, 4, 16, True, 97)])
+@pytest.mark.parametrize("L,s,q,ti,B", [(4, 3, 10, True, 1031), (3, 2, 5, False, 200), (2, 4, 16, True, 97),
+                                        (1, 3, 4, True, 70), (2, 2, 8, True, 300), (3, 5, 6, True, 130),
+                                        (3, 8, 10, True, 150), (5, 2, 4, False, 100), (3, 4, 10, True, 257)])
 def test_philox_sampling_bit_exact_vs_philox_oracle(ops, L, s, q, ti, B):
     """Philox mode: leaves, roots and fused BP must match the NumPy Philox restatement exactly."""
     from oracle import ghm_oracle as O, philox
@@ -167,3 +169,35 @@ def test_host_clip_bayes_matches_device_path(ops):
     ipp64, _ = O.bp_cls(mo.i_T, il.numpy().T, 4, 3, 10, u)
     ref, _ = O.clip_loss(tpp, ipp64, n, K, 10)
     assert sums[0] / n == pytest.approx(ref, rel=1e-5)
+
+
+@pytest.mark.parametrize("L,s,q", [(4, 3, 10), (3, 8, 10), (2, 2, 3)])
+def test_leaf_dtype_alignment_and_tpt_variants_agree(ops, L, s, q):
+    """uint8 / int64 leaves, 16-byte-unaligned leaf views (row-chunk staging path) and odd batch tails must give
+    the same trees and the same posteriors as the aligned int64 call; bp_cls on each form reproduces the fused BP."""
+    from oracle import ghm_oracle as O
+    np.random.seed(11)
+    T = O.gen_transition(L, s, q, 0.2, 1.0, True)
+    m = ops.GhmModel(T, L, s, q, device="cuda:0")
+    B, nL = 333, s ** L
+    ref = m.sample(B, seed=5, root_mode=ops.ROOT_UNIFORM, want_post=True, want_root_hd=True)
+    u8 = m.sample(B, seed=5, root_mode=ops.ROOT_UNIFORM, leaf_dtype=torch.uint8, want_post=True)
+    assert torch.equal(u8["leaves"].long(), ref["leaves"]) and torch.equal(u8["post"], ref["post"])
+    nol = m.sample(B, seed=5, root_mode=ops.ROOT_UNIFORM, want_leaves=False, want_post=True)
+    assert torch.equal(nol["post"], ref["post"]) and torch.equal(nol["root"], ref["root"])
+    # unaligned int64 / uint8 destinations: a view that starts 8 (resp. 1) bytes into an allocation
+    for dt in (torch.int64, torch.uint8):
+        buf = torch.zeros(B * nL + 1, dtype=dt, device="cuda:0")
+        view = buf[1:].view(B, nL)
+        post = torch.empty((B, q), dtype=torch.float32, device="cuda:0")
+        ops.sample_into(m, B, ops.ROOT_UNIFORM, None, 5, 0, None, view, post, None)
+        assert torch.equal(view.long(), ref["leaves"]) and torch.equal(post, ref["post"])
+        assert int(buf[0]) == 0
+        p2, h2 = m.bp_cls(view)
+        np.testing.assert_allclose(p2.cpu().numpy(), ref["post"].cpu().numpy(), rtol=RTOL, atol=1e-7)
+    p3, h3 = m.bp_cls(u8["leaves"])
+    p4, h4 = m.bp_cls(ref["leaves"])
+    assert torch.equal(p3, p4) and torch.equal(h3, h4)
+    np.testing.assert_allclose(p4.cpu().numpy(), ref["post"].cpu().numpy(), rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(h4.cpu().numpy(), ref["root_hd"].cpu().numpy(), rtol=RTOL, atol=2e-5)
+    assert m.status() == 0
