@@ -70,6 +70,12 @@ GHM_API int ghm_device_count(void);
 GHM_API int ghm_model_create(ghm_model_t** out, int n_layer, int n_child, int q, int ti,
                      const double* T_host, const double* p_y_host, int device);
 GHM_API int ghm_model_destroy(ghm_model_t* m);
+/* New tables for an existing model of the same (L, s, q, ti): what constructing a new sampler per p_flip does in
+ * the reference's sweeps (figures/eval-clip-ood.py:76-79, eval-cdm-ood.py:104-109, eval-vlm-ood.py:104-109).
+ * Tables are derived on the host and uploaded with ONE async copy from pinned memory on `stream`
+ * (ghm_model_table_bytes() bytes); kernels enqueued on `stream` afterwards use them. */
+GHM_API int ghm_model_update(ghm_model_t* m, const double* T_host, const double* p_y_host, void* stream);
+GHM_API int64_t ghm_model_table_bytes(const ghm_model_t* m);
 GHM_API int ghm_model_info(const ghm_model_t* m, int* n_layer, int* n_child, int* q, int* ti,
                    int64_t* n_leaves, int64_t* n_edges);
 /* sticky device-side status word (bit0: a leaf/root value >= q was clamped).

@@ -50,7 +50,9 @@ struct GhmDev {
 struct ghm_model {
     GhmDev d;
     int device;
-    float* h_TTp;        // host copy of TTp (source of the constant-bank kernel parameter)
+    void* h_slab;        // pinned host image of the slab (table derivation target, source of H2D uploads)
+    float* h_TTp;        // -> TTp inside h_slab (source of the constant-bank kernel parameter)
+    cudaEvent_t upload_done;
     void* slab;          // single device allocation holding every table
     size_t slab_bytes;
     cudaStream_t stream; // internal stream for ghm_host_* entry points

@@ -42,46 +42,35 @@ extern "C" int ghm_device_count(void) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, const double* T_host,
-                                const double* p_y_host, int device) {
-    if (!out || !T_host) return ghm_fail(GHM_EINVAL, "ghm_model_create: null argument");
-    if (L < 1 || L > GHM_MAX_LEVELS) return ghm_fail(GHM_EINVAL, "n_layer=%d outside [1,%d]", L, GHM_MAX_LEVELS);
-    if (s < 1 || s > 64) return ghm_fail(GHM_EINVAL, "n_child=%d outside [1,64]", s);
-    if (q < 2 || q > 256) return ghm_fail(GHM_EINVAL, "variable_type=%d outside [2,256]", q);
-    double nl = pow((double)s, (double)L);
-    if (nl > 65536.0) return ghm_fail(GHM_EINVAL, "s^L = %.0f leaves is too large (max 65536)", nl);
+// ------------------------------------------------------------------------------------------------
+// table derivation: host slab (pinned) with exactly the device slab's layout
+// ------------------------------------------------------------------------------------------------
+struct SlabLayout {
+    size_t Tlin, TlinT, TlogT, TTp, alias, cdfd, py, rcp, rcu, status, bytes;
+};
 
-    ghm_model* m = new ghm_model();
-    memset(m, 0, sizeof *m);
-    GhmDev& d = m->d;
-    d.L = L; d.s = s; d.q = q; d.ti = ti ? 1 : 0;
-    d.QP = ghm_pad_q(q) ? ghm_pad_q(q) : (int)align_up(q, 4);
-    d.QS = (int)align_up(d.QP, 4);
-    const int QP = d.QP, QS = d.QS;
-    d.spow[0] = 1;
-    for (int l = 1; l <= L; ++l) d.spow[l] = d.spow[l - 1] * s;
-    for (int l = L + 1; l <= GHM_MAX_LEVELS; ++l) d.spow[l] = 0;
-    d.n_leaves = d.spow[L];
-    int e = 0;
-    for (int l = 1; l <= L; ++l) {
-        d.edge_off[l] = e;
-        d.mat_off[l] = d.ti ? (l - 1) * s : e;
-        e += d.spow[l];
-    }
-    d.n_edges = e;
-    d.n_mat = d.ti ? L * s : e;
-    d.s_magic = s >= 2 ? (unsigned)((0x100000000ull + (unsigned)s - 1) / (unsigned)s) : 0u;
-    for (int k = 0; k <= GHM_MAX_LEVELS; ++k)
-        d.pow_magic[k] = (k >= 1 && k <= L && d.spow[k] >= 2)
-                             ? (unsigned)((0x100000000ull + (unsigned)d.spow[k] - 1) / (unsigned)d.spow[k]) : 0u;
-    m->device = device;
+static SlabLayout slab_layout(const GhmDev& d) {
+    SlabLayout o{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t r = off; off = align_up(off + bytes, 256); return r; };
+    const size_t nm = (size_t)d.n_mat, QQ = (size_t)d.QP * d.QP, qq = (size_t)d.q * d.q;
+    o.Tlin = take(nm * QQ * 4); o.TlinT = take(nm * QQ * 4); o.TlogT = take(nm * QQ * 4);
+    o.TTp = take(nm * (size_t)d.QP * d.QS * 4); o.alias = take(nm * qq * 4); o.cdfd = take(nm * qq * 8);
+    o.py = take((size_t)d.QP * 4); o.rcp = take((size_t)d.QP * 4); o.rcu = take((size_t)d.QP * 4);
+    o.status = take(sizeof(int));
+    o.bytes = off;
+    return o;
+}
 
-    // ---- derive the host tables ---------------------------------------------------
+// fills the host slab from the caller's float64 matrices; validates probabilities
+static int derive_tables(const GhmDev& d, const double* T_host, const double* p_y_host, char* hs) {
+    const SlabLayout o = slab_layout(d);
+    const int q = d.q, QP = d.QP, QS = d.QS;
     const size_t nm = (size_t)d.n_mat, QQ = (size_t)QP * QP;
-    std::vector<float> Tlin(nm * QQ, 0.f), TlinT(nm * QQ, 0.f), TlogT(nm * QQ, -INFINITY);
-    std::vector<float> TTp(nm * (size_t)QP * QS, 0.f);
-    std::vector<uint32_t> alias(nm * (size_t)q * q, 0u);
-    std::vector<double> cdfd(nm * (size_t)q * q, 0.0);
+    memset(hs, 0, o.bytes);
+    float* Tlin = (float*)(hs + o.Tlin); float* TlinT = (float*)(hs + o.TlinT); float* TlogT = (float*)(hs + o.TlogT);
+    float* TTp = (float*)(hs + o.TTp); uint32_t* alias = (uint32_t*)(hs + o.alias); double* cdfd = (double*)(hs + o.cdfd);
+    for (size_t i = 0; i < nm * QQ; ++i) TlogT[i] = -INFINITY;
     std::vector<double> scaled(q);
     std::vector<int> small, large;
     for (size_t mi = 0; mi < nm; ++mi) {
@@ -90,10 +79,8 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
             double run = 0.0;
             for (int b = 0; b < q; ++b) {
                 double t = T[(size_t)a * q + b];
-                if (!(t >= 0.0) || !isfinite(t)) {
-                    delete m;
+                if (!(t >= 0.0) || !isfinite(t))
                     return ghm_fail(GHM_EINVAL, "transition[%zu][%d][%d]=%g is not a probability", mi, a, b, t);
-                }
                 Tlin[mi * QQ + (size_t)a * QP + b] = (float)t;
                 TlinT[mi * QQ + (size_t)b * QP + a] = (float)t;
                 TlogT[mi * QQ + (size_t)b * QP + a] = (float)log(t);
@@ -122,29 +109,56 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
             }
         }
     }
-    std::vector<float> py(QP, 0.f);
-    std::vector<uint32_t> rc_prior(QP, 0xFFFFFFFFu), rc_unif(QP, 0xFFFFFFFFu);
-    {
-        double run = 0.0, runu = 0.0;
-        for (int a = 0; a < q; ++a) {
-            double p = p_y_host ? p_y_host[a] : 1.0 / q;
-            if (!(p >= 0.0)) { delete m; return ghm_fail(GHM_EINVAL, "p_y[%d]=%g is not a probability", a, p); }
-            py[a] = (float)p;
-            run += p; runu += 1.0 / q;
-            double t1 = floor(run * 4294967296.0), t2 = floor(runu * 4294967296.0);
-            rc_prior[a] = t1 >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t1;
-            rc_unif[a] = t2 >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t2;
-        }
+    float* py = (float*)(hs + o.py);
+    uint32_t* rc_prior = (uint32_t*)(hs + o.rcp); uint32_t* rc_unif = (uint32_t*)(hs + o.rcu);
+    for (int a = 0; a < QP; ++a) { rc_prior[a] = 0xFFFFFFFFu; rc_unif[a] = 0xFFFFFFFFu; }
+    double run = 0.0, runu = 0.0;
+    for (int a = 0; a < q; ++a) {
+        double p = p_y_host ? p_y_host[a] : 1.0 / q;
+        if (!(p >= 0.0)) return ghm_fail(GHM_EINVAL, "p_y[%d]=%g is not a probability", a, p);
+        py[a] = (float)p;
+        run += p; runu += 1.0 / q;
+        double t1 = floor(run * 4294967296.0), t2 = floor(runu * 4294967296.0);
+        rc_prior[a] = t1 >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t1;
+        rc_unif[a] = t2 >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t2;
     }
+    return GHM_OK;
+}
 
-    // ---- one device slab ----------------------------------------------------------
-    size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    size_t o_Tlin = take(Tlin.size() * 4), o_TlinT = take(TlinT.size() * 4), o_TlogT = take(TlogT.size() * 4);
-    size_t o_TTp = take(TTp.size() * 4), o_alias = take(alias.size() * 4), o_cdfd = take(cdfd.size() * 8);
-    size_t o_py = take(py.size() * 4), o_rcp = take(rc_prior.size() * 4), o_rcu = take(rc_unif.size() * 4);
-    size_t o_status = take(sizeof(int));
-    m->slab_bytes = off;
+extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, const double* T_host,
+                                const double* p_y_host, int device) {
+    if (!out || !T_host) return ghm_fail(GHM_EINVAL, "ghm_model_create: null argument");
+    if (L < 1 || L > GHM_MAX_LEVELS) return ghm_fail(GHM_EINVAL, "n_layer=%d outside [1,%d]", L, GHM_MAX_LEVELS);
+    if (s < 1 || s > 64) return ghm_fail(GHM_EINVAL, "n_child=%d outside [1,64]", s);
+    if (q < 2 || q > 256) return ghm_fail(GHM_EINVAL, "variable_type=%d outside [2,256]", q);
+    double nl = pow((double)s, (double)L);
+    if (nl > 65536.0) return ghm_fail(GHM_EINVAL, "s^L = %.0f leaves is too large (max 65536)", nl);
+
+    ghm_model* m = new ghm_model();
+    memset(m, 0, sizeof *m);
+    GhmDev& d = m->d;
+    d.L = L; d.s = s; d.q = q; d.ti = ti ? 1 : 0;
+    d.QP = ghm_pad_q(q) ? ghm_pad_q(q) : (int)align_up(q, 4);
+    d.QS = (int)align_up(d.QP, 4);
+    d.spow[0] = 1;
+    for (int l = 1; l <= L; ++l) d.spow[l] = d.spow[l - 1] * s;
+    for (int l = L + 1; l <= GHM_MAX_LEVELS; ++l) d.spow[l] = 0;
+    d.n_leaves = d.spow[L];
+    int e = 0;
+    for (int l = 1; l <= L; ++l) {
+        d.edge_off[l] = e;
+        d.mat_off[l] = d.ti ? (l - 1) * s : e;
+        e += d.spow[l];
+    }
+    d.n_edges = e;
+    d.n_mat = d.ti ? L * s : e;
+    d.s_magic = s >= 2 ? (unsigned)((0x100000000ull + (unsigned)s - 1) / (unsigned)s) : 0u;
+    for (int k = 0; k <= GHM_MAX_LEVELS; ++k)
+        d.pow_magic[k] = (k >= 1 && k <= L && d.spow[k] >= 2)
+                             ? (unsigned)((0x100000000ull + (unsigned)d.spow[k] - 1) / (unsigned)d.spow[k]) : 0u;
+    m->device = device;
+    const SlabLayout o = slab_layout(d);
+    m->slab_bytes = o.bytes;
 
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -160,43 +174,57 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     do {                                                                                     \
         cudaError_t _e = (expr);                                                             \
         if (_e != cudaSuccess) {                                                             \
-            if (m->slab) cudaFree(m->slab);                                                  \
             cudaSetDevice(prev);                                                             \
-            delete m;                                                                        \
+            ghm_model_destroy(m);                                                            \
             return ghm_fail(GHM_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));      \
         }                                                                                    \
     } while (0)
     MC_TRY(cudaSetDevice(device));
-    MC_TRY(cudaMalloc(&m->slab, m->slab_bytes));
-    char* base = (char*)m->slab;
-    MC_TRY(cudaMemcpy(base + o_Tlin, Tlin.data(), Tlin.size() * 4, cudaMemcpyHostToDevice));
-    MC_TRY(cudaMemcpy(base + o_TlinT, TlinT.data(), TlinT.size() * 4, cudaMemcpyHostToDevice));
-    MC_TRY(cudaMemcpy(base + o_TlogT, TlogT.data(), TlogT.size() * 4, cudaMemcpyHostToDevice));
-    MC_TRY(cudaMemcpy(base + o_TTp, TTp.data(), TTp.size() * 4, cudaMemcpyHostToDevice));
-    MC_TRY(cudaMemcpy(base + o_alias, alias.data(), alias.size() * 4, cudaMemcpyHostToDevice));
-    MC_TRY(cudaMemcpy(base + o_cdfd, cdfd.data(), cdfd.size() * 8, cudaMemcpyHostToDevice));
-    MC_TRY(cudaMemcpy(base + o_py, py.data(), py.size() * 4, cudaMemcpyHostToDevice));
-    MC_TRY(cudaMemcpy(base + o_rcp, rc_prior.data(), rc_prior.size() * 4, cudaMemcpyHostToDevice));
-    MC_TRY(cudaMemcpy(base + o_rcu, rc_unif.data(), rc_unif.size() * 4, cudaMemcpyHostToDevice));
-    MC_TRY(cudaMemset(base + o_status, 0, sizeof(int)));
+    MC_TRY(cudaMallocHost(&m->h_slab, o.bytes));
+    int rc = derive_tables(d, T_host, p_y_host, (char*)m->h_slab);
+    if (rc) { cudaSetDevice(prev); ghm_model_destroy(m); return rc; }
+    MC_TRY(cudaMalloc(&m->slab, o.bytes));
+    MC_TRY(cudaMemcpy(m->slab, m->h_slab, o.bytes, cudaMemcpyHostToDevice));
     MC_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    MC_TRY(cudaEventCreateWithFlags(&m->upload_done, cudaEventDisableTiming));
     MC_TRY(cudaSetDevice(prev));
 #undef MC_TRY
-    d.Tlin = (const float*)(base + o_Tlin);
-    d.TlinT = (const float*)(base + o_TlinT);
-    d.TlogT = (const float*)(base + o_TlogT);
-    m->h_TTp = (float*)malloc(TTp.size() * sizeof(float));
-    if (m->h_TTp) memcpy(m->h_TTp, TTp.data(), TTp.size() * sizeof(float));
-    d.TTp = (const float*)(base + o_TTp);
-    d.alias = (const uint32_t*)(base + o_alias);
-    d.cdfd = (const double*)(base + o_cdfd);
-    d.py = (const float*)(base + o_py);
-    d.root_cdfu_prior = (const uint32_t*)(base + o_rcp);
-    d.root_cdfu_unif = (const uint32_t*)(base + o_rcu);
-    d.status = (int*)(base + o_status);
+    char* base = (char*)m->slab;
+    d.Tlin = (const float*)(base + o.Tlin);
+    d.TlinT = (const float*)(base + o.TlinT);
+    d.TlogT = (const float*)(base + o.TlogT);
+    d.TTp = (const float*)(base + o.TTp);
+    d.alias = (const uint32_t*)(base + o.alias);
+    d.cdfd = (const double*)(base + o.cdfd);
+    d.py = (const float*)(base + o.py);
+    d.root_cdfu_prior = (const uint32_t*)(base + o.rcp);
+    d.root_cdfu_unif = (const uint32_t*)(base + o.rcu);
+    d.status = (int*)(base + o.status);
+    m->h_TTp = (float*)((char*)m->h_slab + o.TTp);
     *out = m;
     return GHM_OK;
 }
+
+// New tables for an existing model of the same shape (the p_flip sweeps of figures/eval-*-ood.py build a new
+// sampler per p, :76-79): derive on the host, one H2D copy of the slab from pinned memory, enqueued on `stream`.
+// Kernels enqueued on `stream` AFTER this call see the new tables; the caller must not have kernels of this model
+// in flight on OTHER streams.  The sticky status word is preserved.
+extern "C" int ghm_model_update(ghm_model_t* m, const double* T_host, const double* p_y_host, void* stream) {
+    if (!m || !T_host) return ghm_fail(GHM_EINVAL, "ghm_model_update: null argument");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (prev != m->device) cudaSetDevice(m->device);
+    struct Restore { int p, dev; ~Restore() { if (p != dev) cudaSetDevice(p); } } restore{prev, m->device};
+    GHM_CUDA_TRY(cudaEventSynchronize(m->upload_done));          // the previous upload has consumed the pinned slab
+    const SlabLayout o = slab_layout(m->d);
+    int rc = derive_tables(m->d, T_host, p_y_host, (char*)m->h_slab);
+    if (rc) return rc;
+    GHM_CUDA_TRY(cudaMemcpyAsync(m->slab, m->h_slab, o.status, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    GHM_CUDA_TRY(cudaEventRecord(m->upload_done, (cudaStream_t)stream));
+    return GHM_OK;
+}
+
+extern "C" int64_t ghm_model_table_bytes(const ghm_model_t* m) { return m ? (int64_t)slab_layout(m->d).status : 0; }
 
 extern "C" int ghm_model_destroy(ghm_model_t* m) {
     if (!m) return GHM_OK;
@@ -204,10 +232,11 @@ extern "C" int ghm_model_destroy(ghm_model_t* m) {
     cudaGetDevice(&prev);
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->upload_done) cudaEventDestroy(m->upload_done);
     if (m->slab) cudaFree(m->slab);
+    if (m->h_slab) cudaFreeHost(m->h_slab);
     if (m->d_scratch) cudaFree(m->d_scratch);
     if (m->h_scratch) cudaFreeHost(m->h_scratch);
-    free(m->h_TTp);
     cudaSetDevice(prev);
     delete m;
     return GHM_OK;

@@ -20,6 +20,8 @@ SIGNATURES = {
     "ghm_device_count": (c_int, []),
     "ghm_model_create": (c_int, [C.POINTER(c_vp), c_int, c_int, c_int, c_int, c_vp, c_vp, c_int]),
     "ghm_model_destroy": (c_int, [c_vp]),
+    "ghm_model_update": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "ghm_model_table_bytes": (c_i64, [c_vp]),
     "ghm_model_info": (c_int, [c_vp] + [C.POINTER(c_int)] * 4 + [C.POINTER(c_i64)] * 2),
     "ghm_model_status": (c_int, [c_vp, c_vp, C.POINTER(c_int)]),
     "ghm_sample": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_u64, c_u64, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),

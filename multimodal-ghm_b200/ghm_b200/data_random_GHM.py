@@ -416,6 +416,31 @@ class DoubleSampler(_SamplerBase):
         self.t_model._transition_ref = self.t_transition
         self.i_model._transition_ref = self.i_transition
 
+    def reparameterize(self, p_flips, seedtree=None, flip_scale=None, transitions=None):
+        """Swap in the transition tables of another (p_flips, seedtree) IN PLACE: equivalent to constructing a new
+        sampler of the same shape (same NumPy draws: seed, GenTransition text, GenTransition image -- reference
+        :654-658) but re-using the device models (one pinned H2D table copy per modality).  This is what the
+        p_flip sweeps of figures/eval-*-ood.py do once per grid point.  ``transitions=(t, i)`` supplies
+        pre-generated tables instead of drawing them."""
+        self.p_flips = p_flips
+        if seedtree is not None:
+            self.seedtree = seedtree
+        if flip_scale is not None:
+            self.flip_scale = flip_scale
+        if transitions is None:
+            ti = self.t_model.ti
+            np.random.seed(self.seedtree)
+            t_tr = GenTransition(self.n_layers[0], self.n_childs[0], self.variable_type, p_flips[0], self.flip_scale,
+                                 translation_invariance=ti)
+            i_tr = GenTransition(self.n_layers[1], self.n_childs[1], self.variable_type, p_flips[1], self.flip_scale,
+                                 translation_invariance=ti)
+        else:
+            t_tr, i_tr = transitions
+        self.t_transition, self.i_transition = t_tr, i_tr
+        self.t_model.update(t_tr, self.p_ys[0])
+        self.i_model.update(i_tr, self.p_ys[1])
+        return self
+
     # modality 0 = text, 1 = image; the image modality draws from an independent Philox key
     def _tree(self, which, batch_size, root=None, tree_offset=0):
         tr, mo = (self.t_transition, self.t_model) if which == 0 else (self.i_transition, self.i_model)

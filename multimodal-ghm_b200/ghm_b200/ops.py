@@ -57,12 +57,7 @@ class GhmModel:
         self.L, self.s, self.q = int(n_layer), int(n_child), int(variable_type)
         assert len(transition) == self.L
         self.ti = is_translation_invariant(transition, self.s)
-        mats = []
-        for l, level in enumerate(transition):
-            assert len(level) == self.s ** (l + 1), "level %d has %d matrices" % (l, len(level))
-            mats.extend(level[:self.s] if self.ti else level)
-        T = np.ascontiguousarray(np.stack([np.asarray(m, dtype=np.float64) for m in mats]))
-        assert T.shape[1:] == (self.q, self.q)
+        T = self._pack(transition)
         py = None if p_y is None else np.ascontiguousarray(np.asarray(p_y, dtype=np.float64))
         self.n_leaves = self.s ** self.L
         self.n_edges = sum(self.s ** l for l in range(1, self.L + 1))
@@ -72,6 +67,31 @@ class GhmModel:
                                    self.device.index))
         self._h = h
         self._lib = lib
+
+    def _pack(self, transition):
+        """reference list-of-lists -> float64 [n_mat, q, q] (L*s matrices when translation invariant, else E)."""
+        mats = []
+        for l, level in enumerate(transition):
+            assert len(level) == self.s ** (l + 1), "level %d has %d matrices" % (l, len(level))
+            mats.extend(level[:self.s] if self.ti else level)
+        T = np.ascontiguousarray(np.stack([np.asarray(m, dtype=np.float64) for m in mats]))
+        assert T.shape[1:] == (self.q, self.q)
+        return T
+
+    def update(self, transition, p_y=None):
+        """Swap in the tables of another sampler of the same shape (one async H2D copy on the current stream)."""
+        assert len(transition) == self.L and is_translation_invariant(transition, self.s) == self.ti
+        T = self._pack(transition)
+        py = None if p_y is None else np.ascontiguousarray(np.asarray(p_y, dtype=np.float64))
+        with torch.cuda.device(self.device):
+            check(self._lib.ghm_model_update(self._h, T.ctypes.data_as(C.c_void_p),
+                                             py.ctypes.data_as(C.c_void_p) if py is not None else C.c_void_p(0),
+                                             _stream()))
+        self._transition_ref = transition
+
+    @property
+    def table_bytes(self):
+        return int(self._lib.ghm_model_table_bytes(self._h))
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

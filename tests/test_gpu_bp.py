@@ -139,3 +139,26 @@ def test_gauss_noise_matches_philox_oracle_and_is_normal(ops):
     ref = philox.gauss_noise(77, 10, B, s ** L).T
     np.testing.assert_allclose(g, ref, rtol=0, atol=2e-5)
     assert abs(g.mean()) < 5 / np.sqrt(g.size) and abs(g.std() - 1) < 0.01
+
+
+def test_model_update_equals_fresh_model(ops):
+    """ghm_model_update (p_flip sweeps): updated tables give exactly what a freshly created model gives."""
+    from oracle import ghm_oracle as O
+    L, s, q, B = 4, 3, 10, 513
+    np.random.seed(42)
+    T1 = O.gen_transition(L, s, q, 0.2, 1.0, True)
+    np.random.seed(42)
+    T2 = O.gen_transition(L, s, q, 0.06, 1.0, True)
+    py = np.random.dirichlet(np.ones(q))
+    m = ops.GhmModel(T1, L, s, q, p_y=py, device="cuda:0")
+    a1 = m.sample(B, seed=3, root_mode=ops.ROOT_PRIOR, want_post=True, want_root_hd=True)
+    m.update(T2, py)
+    fresh = ops.GhmModel(T2, L, s, q, p_y=py, device="cuda:0")
+    a2, f2 = (x.sample(B, seed=3, root_mode=ops.ROOT_PRIOR, want_post=True, want_root_hd=True) for x in (m, fresh))
+    for k in ("root", "leaves", "post", "root_hd"):
+        assert torch.equal(a2[k], f2[k]), k
+    assert not torch.equal(a1["leaves"], a2["leaves"])
+    z = m.gauss_noise(a2["leaves"], 1.0, seed=9)
+    assert torch.equal(m.bp_dns(z, 1.0, a2["root_hd"]), fresh.bp_dns(z, 1.0, f2["root_hd"]))
+    assert torch.equal(m.bp_nwp(a2["leaves"], a2["root_hd"]), fresh.bp_nwp(f2["leaves"], f2["root_hd"]))
+    assert m.table_bytes > 0 and m.status() == 0
