@@ -45,6 +45,11 @@ extern "C" {
 #define GHM_LEAF_I64  0   /* torch.long, the reference API dtype (data_random_GHM.py:697) */
 #define GHM_LEAF_U8   1   /* compact device format (q <= 256) */
 
+/* arithmetic of the wide-q (16 < q <= 256) row-GEMMs, ghm_model_set_gemm_mode */
+#define GHM_GEMM_F32   0   /* FP32 CUDA cores: <= 1e-5 relative against the float64 reference (default) */
+#define GHM_GEMM_TF32  1   /* tcgen05 kind::tf32, FP32 accumulate in TMEM: <= 2e-3 relative */
+#define GHM_GEMM_BF16  2   /* tcgen05 kind::f16 (BF16 operands), FP32 accumulate: <= 2e-2 relative */
+
 /* root modes for ghm_sample */
 #define GHM_ROOT_GIVEN    0   /* root_in supplied  (reference GHMTree(root=...), :153-156) */
 #define GHM_ROOT_PRIOR    1   /* draw from the model prior p_y (:158) */
@@ -76,6 +81,8 @@ GHM_API int ghm_model_destroy(ghm_model_t* m);
  * (ghm_model_table_bytes() bytes); kernels enqueued on `stream` afterwards use them. */
 GHM_API int ghm_model_update(ghm_model_t* m, const double* T_host, const double* p_y_host, void* stream);
 GHM_API int64_t ghm_model_table_bytes(const ghm_model_t* m);
+/* wide-q models only (ignored for q <= 16): pick the GEMM arithmetic, see GHM_GEMM_* */
+GHM_API int ghm_model_set_gemm_mode(ghm_model_t* m, int mode);
 GHM_API int ghm_model_info(const ghm_model_t* m, int* n_layer, int* n_child, int* q, int* ti,
                    int64_t* n_leaves, int64_t* n_edges);
 /* sticky device-side status word (bit0: a leaf/root value >= q was clamped).
@@ -106,8 +113,9 @@ GHM_API int ghm_sample_mixed(const ghm_model_t* m, int64_t B, int64_t n_given, c
  *   post     : f32 [B, q]  p(root | leaves)               (posterior_probability_CLS^T)
  *   root_hd  : f32 [B, q]  max-shifted log-likelihood, NO prior (root_node.hd_message^T,
  *              the cross-modal "external" message, :871,919)   (either may be NULL) */
+GHM_API int64_t ghm_bp_cls_workspace_bytes(const ghm_model_t* m, int64_t B);   /* 0 for q <= 16 */
 GHM_API int ghm_bp_cls(const ghm_model_t* m, int64_t B, const void* leaves, int leaf_dtype,
-               float* post, float* root_hd, void* stream);
+               float* post, float* root_hd, void* workspace, void* stream);
 
 /* ---- K3: Gaussian denoiser  (GHMTree.BP_DNS, :467-523) -------------------------
  *   z : f32 [B, n_L]; ext : f32 [B, q] external root log-message or NULL;

@@ -26,7 +26,7 @@
 //   cdfd  [m][a][k]   f64  sequential cumsum, unpadded stride q                     (parity mode)
 // ------------------------------------------------------------------------------------
 struct GhmDev {
-    int L, s, q, QP, QS, ti;
+    int L, s, q, QP, QS, QW, ti;                // QW = roundup(q, 64): row stride of the wide (q > 16) path, 0 when q <= 16
     int n_mat;
     int n_leaves;                          // s^L
     int n_edges;                           // sum_{l=1..L} s^l
@@ -39,6 +39,8 @@ struct GhmDev {
     const float* TlinT;
     const float* TlogT;
     const float* TTp;
+    const float* Wup;                      // wide path: [m][a][b] f32 = T[a][b], stride QW, zero padded
+    const float* Wdn;                      // wide path: [m][b][a] f32 = T[a][b], stride QW, zero padded
     const uint32_t* alias;
     const double* cdfd;
     const float* py;                       // [QP] prior, zero padded
@@ -50,6 +52,7 @@ struct GhmDev {
 struct ghm_model {
     GhmDev d;
     int device;
+    int gemm_mode;       // GHM_GEMM_*: arithmetic of the wide path's row-GEMMs
     void* h_slab;        // pinned host image of the slab (table derivation target, source of H2D uploads)
     float* h_TTp;        // -> TTp inside h_slab (source of the constant-bank kernel parameter)
     cudaEvent_t upload_done;

@@ -21,6 +21,7 @@
 #include <algorithm>
 
 #include "ghm_vec.cuh"
+#include "ghm_wide.cuh"
 
 #define DNS_NT 128
 
@@ -246,6 +247,7 @@ __global__ void __launch_bounds__(DNS_NT) k_dns(const GhmDev d, const DnsArgs a)
 // ----------------------------------------------------------------------------------------
 extern "C" int64_t ghm_bp_dns_workspace_bytes(const ghm_model_t* m, int64_t B) {
     if (!m || B <= 0) return 0;
+    if (m->d.QW) return ghm_wide_dns_workspace_bytes(m, B);
     const int Q = ghm_pad_q(m->d.q);
     return std::max<int64_t>(16, (int64_t)m->d.edge_off[m->d.L] * Q * B * (int64_t)sizeof(float));
 }
@@ -281,6 +283,11 @@ extern "C" int ghm_bp_dns(const ghm_model_t* m, int64_t B, const float* z, float
     a.B = B; a.z = z; a.c2 = -0.5f * 1.4426950408889634f / (sigma * sigma); a.ext = ext; a.mean = mean;
     a.scratch = (float*)workspace;
     int rc;
+    if (m->d.QW) {
+        rc = ghm_wide_bp_dns(m, B, z, sigma, ext, mean, workspace, (cudaStream_t)stream);
+        if (prev != m->device) cudaSetDevice(prev);
+        return rc;
+    }
     switch (ghm_pad_q(m->d.q)) {
         case 4: rc = launch_dns<4>(m, a, (cudaStream_t)stream); break;
         case 8: rc = launch_dns<8>(m, a, (cudaStream_t)stream); break;

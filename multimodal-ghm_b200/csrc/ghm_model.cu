@@ -46,7 +46,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // table derivation: host slab (pinned) with exactly the device slab's layout
 // ------------------------------------------------------------------------------------------------
 struct SlabLayout {
-    size_t Tlin, TlinT, TlogT, TTp, alias, cdfd, py, rcp, rcu, status, bytes;
+    size_t Tlin, TlinT, TlogT, TTp, alias, cdfd, Wup, Wdn, py, rcp, rcu, status, bytes;
 };
 
 static SlabLayout slab_layout(const GhmDev& d) {
@@ -56,7 +56,10 @@ static SlabLayout slab_layout(const GhmDev& d) {
     const size_t nm = (size_t)d.n_mat, QQ = (size_t)d.QP * d.QP, qq = (size_t)d.q * d.q;
     o.Tlin = take(nm * QQ * 4); o.TlinT = take(nm * QQ * 4); o.TlogT = take(nm * QQ * 4);
     o.TTp = take(nm * (size_t)d.QP * d.QS * 4); o.alias = take(nm * qq * 4); o.cdfd = take(nm * qq * 8);
-    o.py = take((size_t)d.QP * 4); o.rcp = take((size_t)d.QP * 4); o.rcu = take((size_t)d.QP * 4);
+    const size_t WW = (size_t)d.QW * d.QW;
+    o.Wup = take(nm * WW * 4); o.Wdn = take(nm * WW * 4);
+    const size_t PW = (size_t)(d.QW > d.QP ? d.QW : d.QP);
+    o.py = take(PW * 4); o.rcp = take((size_t)d.QP * 4); o.rcu = take((size_t)d.QP * 4);
     o.status = take(sizeof(int));
     o.bytes = off;
     return o;
@@ -69,6 +72,7 @@ static int derive_tables(const GhmDev& d, const double* T_host, const double* p_
     const size_t nm = (size_t)d.n_mat, QQ = (size_t)QP * QP;
     memset(hs, 0, o.bytes);
     float* Tlin = (float*)(hs + o.Tlin); float* TlinT = (float*)(hs + o.TlinT); float* TlogT = (float*)(hs + o.TlogT);
+    float* Wup = (float*)(hs + o.Wup); float* Wdn = (float*)(hs + o.Wdn);
     float* TTp = (float*)(hs + o.TTp); uint32_t* alias = (uint32_t*)(hs + o.alias); double* cdfd = (double*)(hs + o.cdfd);
     for (size_t i = 0; i < nm * QQ; ++i) TlogT[i] = -INFINITY;
     std::vector<double> scaled(q);
@@ -85,6 +89,10 @@ static int derive_tables(const GhmDev& d, const double* T_host, const double* p_
                 TlinT[mi * QQ + (size_t)b * QP + a] = (float)t;
                 TlogT[mi * QQ + (size_t)b * QP + a] = (float)log(t);
                 TTp[mi * (size_t)QP * QS + (size_t)b * QS + a] = (float)t;
+                if (d.QW) {
+                    Wup[mi * (size_t)d.QW * d.QW + (size_t)a * d.QW + b] = (float)t;
+                    Wdn[mi * (size_t)d.QW * d.QW + (size_t)b * d.QW + a] = (float)t;
+                }
                 run = (b == 0) ? t : run + t;                 // np.cumsum: sequential f64 adds
                 cdfd[mi * (size_t)q * q + (size_t)a * q + b] = run;
             }
@@ -140,6 +148,7 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     d.L = L; d.s = s; d.q = q; d.ti = ti ? 1 : 0;
     d.QP = ghm_pad_q(q) ? ghm_pad_q(q) : (int)align_up(q, 4);
     d.QS = (int)align_up(d.QP, 4);
+    d.QW = q > GHM_MAX_Q_REG ? (int)align_up(q, 64) : 0;
     d.spow[0] = 1;
     for (int l = 1; l <= L; ++l) d.spow[l] = d.spow[l - 1] * s;
     for (int l = L + 1; l <= GHM_MAX_LEVELS; ++l) d.spow[l] = 0;
@@ -194,6 +203,8 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     d.TlinT = (const float*)(base + o.TlinT);
     d.TlogT = (const float*)(base + o.TlogT);
     d.TTp = (const float*)(base + o.TTp);
+    d.Wup = (const float*)(base + o.Wup);
+    d.Wdn = (const float*)(base + o.Wdn);
     d.alias = (const uint32_t*)(base + o.alias);
     d.cdfd = (const double*)(base + o.cdfd);
     d.py = (const float*)(base + o.py);
@@ -221,6 +232,14 @@ extern "C" int ghm_model_update(ghm_model_t* m, const double* T_host, const doub
     if (rc) return rc;
     GHM_CUDA_TRY(cudaMemcpyAsync(m->slab, m->h_slab, o.status, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     GHM_CUDA_TRY(cudaEventRecord(m->upload_done, (cudaStream_t)stream));
+    return GHM_OK;
+}
+
+extern "C" int ghm_model_set_gemm_mode(ghm_model_t* m, int mode) {
+    if (!m) return ghm_fail(GHM_EINVAL, "ghm_model_set_gemm_mode: null model");
+    if (mode != GHM_GEMM_F32 && mode != GHM_GEMM_TF32 && mode != GHM_GEMM_BF16)
+        return ghm_fail(GHM_EINVAL, "ghm_model_set_gemm_mode: bad mode %d", mode);
+    m->gemm_mode = mode;
     return GHM_OK;
 }
 

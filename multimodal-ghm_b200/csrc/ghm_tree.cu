@@ -3,6 +3,7 @@
 // Replaces GHMTree.gen_values (src/ghmclip/data/data_random_GHM.py:145-165) and GHMTree.BP_CLS (:185-221) of the
 // reference.  The Philox sampler / BP kernel template is in ghm_tree_kernel.cuh (design notes there).
 #include "ghm_tree_kernel.cuh"
+#include "ghm_wide.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // k_sample_parity: reference uniforms, f64 compare, one thread per tree, level by level down each
@@ -74,7 +75,10 @@ GHM_TREE_DECLARE_ALL(16)
             return ghm_fail(GHM_EUNSUP, "variable_type=%d: register-resident kernels cover q <= %d in this build", \
                             m->d.q, GHM_MAX_Q_REG);                                                               \
     }
-static int run_sample(const ghm_model* m, const TreeArgs& a, cudaStream_t st) { GHM_TREE_SWITCH(s) }
+static int run_sample(const ghm_model* m, const TreeArgs& a, cudaStream_t st) {
+    if (m->d.q > GHM_MAX_Q_REG) return ghm_tree_run_q4_s(m, a, st);   // sampling never touches a q-vector: any instantiation serves
+    GHM_TREE_SWITCH(s)
+}
 static int run_sample_bp(const ghm_model* m, const TreeArgs& a, cudaStream_t st) { GHM_TREE_SWITCH(sb) }
 static int run_given_bp(const ghm_model* m, const TreeArgs& a, cudaStream_t st) { GHM_TREE_SWITCH(g) }
 
@@ -101,6 +105,9 @@ static int sample_common(const ghm_model_t* m, int64_t B, int root_mode, int64_t
     a.tree_offset = tree_offset;
     a.root_out = root_out; a.leaves = leaves_out; a.leaf_dtype = leaf_dtype; a.post = post_out; a.root_hd = root_hd_out;
     const bool bp = post_out || root_hd_out;
+    if (bp && m->d.QW)
+        return ghm_fail(GHM_EUNSUP, "ghm_sample: fused BP covers q <= %d; for q = %d sample, then call ghm_bp_cls", GHM_MAX_Q_REG,
+                        m->d.q);
     cudaStream_t st = (cudaStream_t)stream;
     if (U) {
         if (bp) return ghm_fail(GHM_EINVAL, "ghm_sample: fused BP is a Philox-mode feature; in parity mode call ghm_bp_cls");
@@ -126,12 +133,18 @@ extern "C" int ghm_sample_mixed(const ghm_model_t* m, int64_t B, int64_t n_given
                          leaf_dtype, post_out, root_hd_out, stream);
 }
 
+extern "C" int64_t ghm_bp_cls_workspace_bytes(const ghm_model_t* m, int64_t B) {
+    if (!m || B <= 0 || m->d.QW == 0) return 0;
+    return ghm_wide_cls_workspace_bytes(m, B);
+}
+
 extern "C" int ghm_bp_cls(const ghm_model_t* m, int64_t B, const void* leaves, int leaf_dtype, float* post,
-                          float* root_hd, void* stream) {
+                          float* root_hd, void* workspace, void* stream) {
     if (!m || !leaves) return ghm_fail(GHM_EINVAL, "ghm_bp_cls: null argument");
     if (B <= 0) return B == 0 ? GHM_OK : ghm_fail(GHM_EINVAL, "ghm_bp_cls: negative batch");
     if (leaf_dtype != GHM_LEAF_I64 && leaf_dtype != GHM_LEAF_U8) return ghm_fail(GHM_EINVAL, "bad leaf_dtype %d", leaf_dtype);
     DeviceGuard g(m->device);
+    if (m->d.QW) return ghm_wide_bp_cls(m, B, leaves, leaf_dtype, post, root_hd, workspace, (cudaStream_t)stream);
     TreeArgs a{};
     a.B = B; a.leaves = const_cast<void*>(leaves); a.leaf_dtype = leaf_dtype; a.post = post; a.root_hd = root_hd;
     return run_given_bp(m, a, (cudaStream_t)stream);

@@ -94,7 +94,10 @@ __device__ __forceinline__ int ghm_search_u32(const uint32_t* __restrict__ row, 
 
 // parity-mode inverse CDF: first k with u < cdf[k], else 0   (reference argmax semantics, :164-165)
 __device__ __forceinline__ int ghm_search_f64(const double* __restrict__ row, double u, int q) {
-    int cnt = 0;
-    for (int k = 0; k < q; ++k) cnt += (u >= __ldg(row + k)) ? 1 : 0;
-    return cnt == q ? 0 : cnt;
+    int lo = 0, hi = q;                                  // cdf is non-decreasing: lower bound of {k : u < cdf[k]}
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (u >= __ldg(row + mid)) lo = mid + 1; else hi = mid;
+    }
+    return lo == q ? 0 : lo;
 }

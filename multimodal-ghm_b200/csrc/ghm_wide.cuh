@@ -1,0 +1,16 @@
+// ghm_wide.cuh -- internal interface of the wide (16 < q <= 256) belief-propagation path.
+#pragma once
+#include "ghm_common.cuh"
+
+int64_t ghm_wide_cls_workspace_bytes(const ghm_model* m, int64_t B);
+int ghm_wide_bp_cls(const ghm_model* m, int64_t B, const void* leaves, int leaf_dtype, float* post, float* root_hd,
+                    void* workspace, cudaStream_t st);
+int64_t ghm_wide_dns_workspace_bytes(const ghm_model* m, int64_t B);
+int ghm_wide_bp_dns(const ghm_model* m, int64_t B, const float* z, float sigma, const float* ext, float* mean,
+                    void* workspace, cudaStream_t st);
+
+// Y[node][b][:] = X[node][b][:] @ W[mat(level, node)]  for the n_nodes nodes of `level`;
+// down = 0: W[k][n] = T[n][k] (child -> parent, `T @ m`), down = 1: W[k][n] = T[k][n] (parent -> child, `T.T @ m`)
+int ghm_wide_gemm(const ghm_model* m, int64_t B, int level, int n_nodes, int down, const float* X, float* Y, cudaStream_t st);
+// tcgen05 TF32 / BF16 variant (ghm_wide_tc.cu); returns GHM_EUNSUP for shapes it does not cover
+int ghm_wide_gemm_tc(const ghm_model* m, int64_t B, int level, int n_nodes, int down, const float* X, float* Y, cudaStream_t st);

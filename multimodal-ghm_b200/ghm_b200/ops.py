@@ -101,6 +101,12 @@ class GhmModel:
             except Exception:
                 pass
 
+    GEMM_F32, GEMM_TF32, GEMM_BF16 = 0, 1, 2
+
+    def set_gemm_mode(self, mode):
+        """Arithmetic of the wide-q (q > 16) row-GEMMs: GEMM_F32 (CUDA cores, default), GEMM_TF32 / GEMM_BF16 (tcgen05)."""
+        check(self._lib.ghm_model_set_gemm_mode(self._h, int(mode)))
+
     def status(self):
         out = C.c_int(0)
         with torch.cuda.device(self.device):
@@ -145,7 +151,10 @@ class GhmModel:
         with torch.cuda.device(self.device):
             post = torch.empty((B, self.q), dtype=torch.float32, device=self.device)
             hd = torch.empty((B, self.q), dtype=torch.float32, device=self.device)
-            check(self._lib.ghm_bp_cls(self._h, B, _ptr(leaves), _leaf_code(leaves), _ptr(post), _ptr(hd), _stream()))
+            nws = self._lib.ghm_bp_cls_workspace_bytes(self._h, B)
+            ws = self._workspace(nws) if nws > 0 else None
+            check(self._lib.ghm_bp_cls(self._h, B, _ptr(leaves), _leaf_code(leaves), _ptr(post), _ptr(hd), _ptr(ws),
+                                       _stream()))
         return post, hd
 
     # ---- K3 ---------------------------------------------------------------------------

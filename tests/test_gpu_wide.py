@@ -1,0 +1,67 @@
+"""Wide path (16 < q <= 256): sampling for any q, level-synchronous row-GEMM BP_CLS / BP_DNS, through the C ABI.
+
+FP32 CUDA-core GEMMs must match the float64 oracle to 1e-5 relative like the register-resident kernels;
+the tcgen05 TF32 / BF16 variants are held to their stated looser bounds.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ghm_b200 import ops as _ops
+    return _ops
+
+
+def _model(ops, L, s, q, ti, seed=3, p=0.25):
+    from oracle import ghm_oracle as O
+    np.random.seed(seed)
+    T = O.gen_transition(L, s, q, p, 1.0, ti)
+    py = np.random.dirichlet(np.ones(q) * 2)
+    return T, py, ops.GhmModel(T, L, s, q, p_y=py, device="cuda:0")
+
+
+@pytest.mark.parametrize("L,s,q,ti,B", [(3, 3, 20, True, 300), (2, 2, 32, False, 129), (3, 2, 64, True, 257),
+                                        (2, 3, 100, True, 150), (2, 2, 256, True, 131)])
+def test_wide_sampling_and_bp_cls_vs_oracle(ops, L, s, q, ti, B):
+    from oracle import ghm_oracle as O, philox
+    T, py, m = _model(ops, L, s, q, ti)
+    rng = np.random.RandomState(1)
+    root = rng.randint(0, q, size=B)
+    U = rng.rand(O.n_edges(L, s), B)
+    vals = O.sample_tree(T, L, s, q, B, root=root, U=U)
+    out = m.sample(B, root=root, U=torch.from_numpy(U).cuda())
+    assert np.array_equal(out["leaves"].cpu().numpy(), vals[-1].T)              # parity mode: bit-exact
+    pv = philox.sample_tree_philox(T, L, s, q, B, 77, tree_offset=5, p_y=py)
+    po = m.sample(B, seed=77, tree_offset=5, root_mode=ops.ROOT_PRIOR)
+    assert np.array_equal(po["root"].cpu().numpy(), pv[0][0])
+    assert np.array_equal(po["leaves"].cpu().numpy(), pv[-1].T)                 # Philox mode: bit-exact vs the restatement
+    post, hd = O.bp_cls(T, vals[-1], L, s, q, py)
+    p, h = m.bp_cls(out["leaves"])
+    np.testing.assert_allclose(p.cpu().numpy(), post.T, rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(h.cpu().numpy(), hd[0][0].T, rtol=RTOL, atol=2e-5)
+    p8, _ = m.bp_cls(out["leaves"].to(torch.uint8))
+    assert torch.equal(p8, p)
+    assert m.status() == 0
+
+
+@pytest.mark.parametrize("L,s,q,ti,B,sigma", [(3, 3, 20, True, 200, 1.0), (2, 2, 32, False, 129, 0.5), (3, 2, 64, True, 140, 2.0),
+                                              (2, 2, 256, True, 70, 1.0)])
+def test_wide_bp_dns_vs_oracle(ops, L, s, q, ti, B, sigma):
+    from oracle import ghm_oracle as O
+    T, py, m = _model(ops, L, s, q, ti, seed=5)
+    rng = np.random.RandomState(2)
+    vals = O.sample_tree(T, L, s, q, B, root=rng.randint(0, q, size=B), U=rng.rand(O.n_edges(L, s), B))
+    z = vals[-1] + sigma * rng.randn(s ** L, B)
+    ext = np.log(rng.dirichlet(np.ones(q), size=B).T)                           # (q, B) log-message
+    for e in (None, ext):
+        ref = O.bp_dns(T, z, sigma, L, s, q, ext=e)
+        mean_ref = ref[0] if isinstance(ref, tuple) else ref
+        zt = torch.from_numpy(z.T.astype(np.float32)).cuda().contiguous()
+        et = None if e is None else torch.from_numpy(e.T.astype(np.float32)).cuda().contiguous()
+        got = m.bp_dns(zt, sigma, et).cpu().numpy()
+        np.testing.assert_allclose(got, np.asarray(mean_ref).T, rtol=2e-5, atol=2e-5 * q)
