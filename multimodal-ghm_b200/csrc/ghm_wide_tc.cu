@@ -1,4 +1,234 @@
-// ghm_wide_tc.cu -- tcgen05 variant of the wide path's batched row-GEMM (placeholder until the UMMA kernel lands).
+// ghm_wide_tc.cu -- tcgen05 (5th-gen tensor core) variant of the wide path's batched row-GEMM.
+//
+//   Y[node][b][n] = sum_k X[node][b][k] * Wk[mat(node)][n][k]        (both operands K-major)
+//
+// i.e. the [B*nodes, q] x [q, q] contraction of the north star, used only when q is large (QW in
+// {64, 128, 192, 256}) and the model's gemm mode asks for it (GHM_GEMM_TF32 / GHM_GEMM_BF16; the default is
+// the FP32 CUDA-core kernel in ghm_wide.cu).  Child -> parent (`T @ m`, reference :207,497): Wk = Wup
+// (row a, contiguous b); parent -> child (`T.T @ m`, :513): Wk = Wdn.
+//
+// One CTA = one 128-tree x QW output tile of one node:
+//   * operands are staged in shared memory in the canonical K-major SWIZZLE_128B layout (rows of 128 bytes,
+//     8-row / 1024-byte atoms, 16-byte chunk index XOR row%8) by all 128 threads -- TF32 takes the FP32
+//     messages as they are, BF16 converts on the fly -- double/triple buffered over 128-byte K chunks;
+//   * one elected thread issues tcgen05.mma (M = 128, N = QW, K = 8 (tf32) / 16 (bf16) per instruction, four
+//     per chunk, descriptor start address advanced by 32 bytes inside the swizzle atom), accumulating FP32 in
+//     TMEM; tcgen05.commit arrives on the stage's mbarrier so the stage can be refilled while later MMAs run;
+//   * epilogue: each warp reads its 32 TMEM lanes with tcgen05.ld.32x32b.x32 and writes full 128-byte row
+//     segments of Y.
+// The combine / cavity / belief row kernels around the GEMM are shared with the FP32 path.
 #include "ghm_wide.cuh"
 
-int ghm_wide_gemm_tc(const ghm_model*, int64_t, int, int, int, const float*, float*, cudaStream_t) { return GHM_EUNSUP; }
+#include <cuda_bf16.h>
+
+#define TC_THREADS 128
+#define TC_M 128
+#define TC_MAX_STAGES 3
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1, SBO = 1024 B between 8-row atoms)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t desc = 0;
+    desc |= (uint64_t)((saddr >> 4) & 0x3FFF);            // start address, bits [0,14)
+    desc |= (uint64_t)0 << 16;                             // leading byte offset (unused: K extent <= one swizzle row)
+    desc |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset, bits [32,46)
+    desc |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+    desc |= (uint64_t)2 << 61;                             // layout type SWIZZLE_128B
+    return desc;
+}
+
+template <int KIND>
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (KIND == GHM_GEMM_TF32) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+
+// store one 128-byte operand row (eight 16-byte chunks) at row r of a SWIZZLE_128B tile
+__device__ __forceinline__ void st_row_sw128(unsigned char* tile, int r, const uint4 (&c)[8]) {
+    unsigned char* row = tile + (size_t)r * 128;
+    const int x = r & 7;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(row + ((j ^ x) << 4)) = c[j];
+}
+
+// fetch the 128-byte operand row for K chunk kc from an FP32 source row (null -> zeros)
+template <int KIND>
+__device__ __forceinline__ void load_row(const float* __restrict__ src, int kc, uint4 (&c)[8]) {
+    if (!src) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    if constexpr (KIND == GHM_GEMM_TF32) {                  // 32 floats, used as they are (tf32 = the top 19 bits)
+        const uint4* p = reinterpret_cast<const uint4*>(src + kc * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = __ldg(p + j);
+    } else {                                                // 64 floats -> 64 bf16
+        const float4* p = reinterpret_cast<const float4*>(src + kc * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 a = __ldg(p + 2 * j), b = __ldg(p + 2 * j + 1);
+            __nv_bfloat162 v0 = __floats2bfloat162_rn(a.x, a.y), v1 = __floats2bfloat162_rn(a.z, a.w);
+            __nv_bfloat162 v2 = __floats2bfloat162_rn(b.x, b.y), v3 = __floats2bfloat162_rn(b.z, b.w);
+            c[j] = make_uint4(*reinterpret_cast<uint32_t*>(&v0), *reinterpret_cast<uint32_t*>(&v1),
+                              *reinterpret_cast<uint32_t*>(&v2), *reinterpret_cast<uint32_t*>(&v3));
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(TC_THREADS) k_wide_gemm_tc(const GhmDev d, int64_t B, int level, int down, int stages,
+                                                             const float* __restrict__ X, float* __restrict__ Y) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[TC_MAX_STAGES];
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = d.QW;                                     // 64 / 128 / 192 / 256
+    const int node = blockIdx.y;
+    const int64_t m0 = (int64_t)blockIdx.x * TC_M;
+    const int mi = d.mat_off[level] + (d.ti ? node - ghm_div_s(node, d) * d.s : node);
+    const float* Wk = (down ? d.Wdn : d.Wup) + (size_t)mi * N * N;            // [n][k]
+    const float* Xn = X + (int64_t)node * B * N;
+    float* Yn = Y + (int64_t)node * B * N;
+
+    unsigned char* tiles = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = TC_M * 128, b_bytes = N * 128, stage_bytes = a_bytes + b_bytes;
+    const int kchunk = KIND == GHM_GEMM_TF32 ? 32 : 64;
+    const int nchunks = N / kchunk;
+    const uint32_t tmem_cols = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+
+    if (tid == 0) {
+        for (int i = 0; i < TC_MAX_STAGES; ++i) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+
+    // instruction descriptor: D = F32, A/B = TF32 or BF16, both K-major, N, M = 128
+    const uint32_t fmt = KIND == GHM_GEMM_TF32 ? 2u : 1u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+    const int64_t arow = m0 + tid;                          // thread t stages A row t and B rows t, t+128
+    const float* asrc = arow < B ? Xn + arow * N : nullptr;
+
+    for (int kc = 0; kc < nchunks; ++kc) {
+        const int st = kc % stages;
+        unsigned char* At = tiles + (size_t)st * stage_bytes;
+        unsigned char* Bt = At + a_bytes;
+        if (kc >= stages) mbar_wait(&bars[st], ((kc / stages) - 1) & 1);      // the MMAs that read this stage are done
+        uint4 c[8];
+        load_row<KIND>(asrc, kc, c);
+        st_row_sw128(At, tid, c);
+        for (int n = tid; n < N; n += TC_THREADS) {
+            load_row<KIND>(Wk + (size_t)n * N, kc, c);
+            st_row_sw128(Bt, n, c);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> async proxy (UMMA)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t adesc = umma_desc_sw128(smem_u32(At)), bdesc = umma_desc_sw128(smem_u32(Bt));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)                                         // 4 x 32 bytes of K per 128-byte chunk
+                umma_issue<KIND>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[st]))
+                         : "memory");
+        }
+    }
+    // wait for the last commit of every stage in flight (commits complete in issue order: the last one suffices)
+    {
+        const int kc = nchunks - 1, st = kc % stages;
+        mbar_wait(&bars[st], (kc / stages) & 1);
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: TMEM -> registers -> global (row m0 + 32*warp + lane, 32 columns at a time) ----
+    const int64_t row = m0 + warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < B) {
+            uint4* dst = reinterpret_cast<uint4*>(Yn + row * N + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+}
+
+int ghm_wide_gemm_tc(const ghm_model* m, int64_t B, int level, int n_nodes, int down, const float* X, float* Y, cudaStream_t st) {
+    const GhmDev& d = m->d;
+    const int N = d.QW;
+    if (N != 64 && N != 128 && N != 192 && N != 256) return GHM_EUNSUP;
+    if (n_nodes > 65535) return GHM_EUNSUP;
+    const int kind = m->gemm_mode;
+    const int kchunk = kind == GHM_GEMM_TF32 ? 32 : 64;
+    const int nchunks = N / kchunk;
+    const int stage_bytes = TC_M * 128 + N * 128;
+    int stages = std::min(TC_MAX_STAGES, nchunks);
+    while (stages > 1 && (size_t)stages * stage_bytes + 1024 > 200 * 1024) --stages;
+    const size_t dyn = (size_t)stages * stage_bytes + 1024;
+    dim3 grid((unsigned)((B + TC_M - 1) / TC_M), (unsigned)n_nodes);
+    if (kind == GHM_GEMM_TF32) {
+        GHM_CUDA_TRY(cudaFuncSetAttribute(k_wide_gemm_tc<GHM_GEMM_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        k_wide_gemm_tc<GHM_GEMM_TF32><<<grid, TC_THREADS, dyn, st>>>(d, B, level, down, stages, X, Y);
+    } else if (kind == GHM_GEMM_BF16) {
+        GHM_CUDA_TRY(cudaFuncSetAttribute(k_wide_gemm_tc<GHM_GEMM_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        k_wide_gemm_tc<GHM_GEMM_BF16><<<grid, TC_THREADS, dyn, st>>>(d, B, level, down, stages, X, Y);
+    } else {
+        return GHM_EUNSUP;
+    }
+    GHM_CHECK_LAUNCH();
+    return GHM_OK;
+}

@@ -65,3 +65,30 @@ def test_wide_bp_dns_vs_oracle(ops, L, s, q, ti, B, sigma):
         et = None if e is None else torch.from_numpy(e.T.astype(np.float32)).cuda().contiguous()
         got = m.bp_dns(zt, sigma, et).cpu().numpy()
         np.testing.assert_allclose(got, np.asarray(mean_ref).T, rtol=2e-5, atol=2e-5 * q)
+
+
+@pytest.mark.parametrize("L,s,q,B", [(3, 2, 64, 300), (2, 3, 128, 200), (2, 2, 180, 129), (2, 2, 256, 260)])
+@pytest.mark.parametrize("mode,tol", [("tf32", 3e-3), ("bf16", 3e-2)])
+def test_wide_tcgen05_gemm_variants(ops, L, s, q, B, mode, tol):
+    """tcgen05 TF32 / BF16 row-GEMMs (FP32 accumulation in TMEM) against the float64 oracle at their stated
+    looser bound, and against the FP32 CUDA-core path of the same library."""
+    from oracle import ghm_oracle as O
+    T, py, m = _model(ops, L, s, q, True, seed=9, p=0.3)
+    rng = np.random.RandomState(4)
+    vals = O.sample_tree(T, L, s, q, B, root=rng.randint(0, q, size=B), U=rng.rand(O.n_edges(L, s), B))
+    leaves = torch.from_numpy(vals[-1].T.copy()).cuda()
+    z = torch.from_numpy((vals[-1] + rng.randn(s ** L, B)).T.astype(np.float32)).cuda().contiguous()
+    p32, h32 = m.bp_cls(leaves)
+    mean32 = m.bp_dns(z, 1.0, h32)
+    m.set_gemm_mode(m.GEMM_TF32 if mode == "tf32" else m.GEMM_BF16)
+    ptc, htc = m.bp_cls(leaves)
+    meantc = m.bp_dns(z, 1.0, h32)
+    torch.cuda.synchronize()
+    assert not torch.equal(ptc, p32), "tensor-core mode produced bit-identical results: it did not run"
+    post, hd = O.bp_cls(T, vals[-1], L, s, q, py)
+    np.testing.assert_allclose(ptc.cpu().numpy(), post.T, rtol=tol, atol=tol * 1e-3)
+    np.testing.assert_allclose(ptc.cpu().numpy(), p32.cpu().numpy(), rtol=tol, atol=tol * 1e-3)
+    np.testing.assert_allclose(meantc.cpu().numpy(), mean32.cpu().numpy(), rtol=tol, atol=tol * q * 0.05)
+    m.set_gemm_mode(m.GEMM_F32)
+    p_again, _ = m.bp_cls(leaves)
+    assert torch.equal(p_again, p32)
