@@ -11,13 +11,15 @@ symmetric K-way Bayes contrastive reduction -> {sum, sumsq, count}; N > 1: every
 own 65 536 pairs (weak scaling; Philox tree offsets = rank * B) and the 24-byte sums are
 all-reduced over NCCL each step.
 
-`value`  : device-resident trees/s (CUDA events around exactly K steps, max over ranks).
-`e2e`    : the same metric through the reference-facing call ClipSampler.get_Bayes(n_eval)
-           (host call -> host floats; the facade draws nothing on the host in Philox mode, so the
-           H2D traffic is the kernel arguments only and the D2H read is the 24-byte risk sums).
-`e2e_get_batch`: as above but ALSO delivering what ClipSampler.get_batch returns (int64 leaves and
-           f32 posteriors of both modalities) into pinned host memory.
-`roofline`: dominant kernel = fused sampler+BP k_tree; algorithmic bytes = int64 leaves + roots +
+`value`  : device-resident trees/s (CUDA events around exactly K steps, max over ranks).  N > 1: the 24-byte
+           all-reduce of step k runs on NCCL's stream and overlaps the kernels of the following steps (ring of
+           accumulators); every all-reduce has joined the compute stream before the closing event.
+`e2e`    : one step = one grid point of the reference's p_flip sweep (figures/eval-clip-ood.py:73-79): new float64
+           transition matrices come from the host, derived tables are built in pinned memory and uploaded
+           (ghm_model_update), then ClipSampler.get_Bayes(n_eval) returns two host floats (24-byte D2H read).
+`e2e_get_batch`: get_Bayes plus what ClipSampler.get_batch returns (int64 leaves and f32 posteriors of both
+           modalities) copied into pinned host memory through the host-buffer C entry point (PCIe bound).
+`roofline`: dominant kernel = fused sampler+BP k_tree2; algorithmic bytes = int64 leaves + roots +
            f32 posterior per tree (K1 656 B + K2 40 B out), timed with CUDA events per launch.
 `cpu_baseline` / `--impl reference`: the NumPy oracle port of the reference algorithm
            (oracle/ghm_oracle.py, pinned to the reference's fixtures) fanned out over all host cores.
@@ -205,11 +207,22 @@ def run_ours(args, rank, world, local_rank):
     t_root = torch.empty(B, dtype=torch.int64, device=dev)
     t_pp = torch.empty((B, Q), dtype=torch.float32, device=dev)
     i_pp = torch.empty((B, Q), dtype=torch.float32, device=dev)
-    sums = torch.zeros(3, dtype=torch.float64, device=dev)
+    # Risk accumulators: a ring, so the 24-byte all-reduce of step k (NCCL's own stream) overlaps the kernels of
+    # step k+1.. instead of serialising ~40 us of collective latency into every 0.36 ms step.
+    RING = 8
+    sums_ring = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(RING)]
+    works = [None] * RING
+    step_no = [0]
     kern_events = []
 
-    def step(seed, record=False):
+    def step(seed, record=False, reduce=True):
         """sample text / image (+ fused BP, leaves materialised), contrastive reduction, all-reduce of the sums."""
+        slot = step_no[0] % RING
+        step_no[0] += 1
+        sums = sums_ring[slot]
+        if works[slot] is not None:
+            works[slot].wait()                           # the all-reduce that last used this slot (8 steps ago) is done
+            works[slot] = None
         sums.zero_()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if record else None
         if record: evs[0].record()
@@ -218,10 +231,17 @@ def run_ours(args, rank, world, local_rank):
         ops.sample_mixed_into(im, B, 2 * n, t_root, seed ^ ops.IMAGE_SEED_XOR, tree_off, None, i_leaves, i_pp, None)
         if record: evs[2].record()
         ops.risk_clip(t_pp, i_pp, n, K, Q, sums=sums)
-        if world > 1:
-            dist.all_reduce(sums)
+        if world > 1 and reduce:
+            works[slot] = dist.all_reduce(sums, async_op=True)
         if record:
             kern_events.append(evs)
+        return sums
+
+    def drain():
+        for i, w in enumerate(works):
+            if w is not None:
+                w.wait()
+                works[i] = None
 
     def barrier():
         if world > 1:
@@ -230,14 +250,17 @@ def run_ours(args, rank, world, local_rank):
 
     for w in range(args.warmup):
         step(100 + w)
+    drain()
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    last = None
     for k in range(args.steps):
-        step(1000 + k, record=True)
+        last = step(1000 + k, record=True)
+    drain()                                              # every all-reduce has joined the compute stream before e1
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -245,12 +268,12 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    risk_mean, risk_se = ops.mean_se(sums)
+    risk_mean, risk_se = ops.mean_se(last)
     # keep the GPU busy while the clock sampler gets enough samples if the run was very short
     if rank == 0 and ms < 1500:
         t_end = time.time() + 1.5
         while time.time() < t_end:
-            step(5000)
+            step(5000, reduce=False)                     # rank 0 only: no collective in here
         torch.cuda.synchronize()
     clk = clocks.stop() if rank == 0 else None
     value = world * trees_step * args.steps / (ms * 1e-3)

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--leaf", default="i64", choices=["i64", "u8", "none"])
     ap.add_argument("--non-ti", action="store_true")
     ap.add_argument("--sigma", type=float, default=1.0)
+    ap.add_argument("--gemm", default="f32", choices=["f32", "tf32", "bf16"], help="wide-q (q > 16) GEMM arithmetic")
     a = ap.parse_args()
     import torch
     from ghm_b200 import ops
@@ -36,6 +37,7 @@ def main():
     T = GenTransition(a.L, a.s, a.q, 0.2, 1.0, translation_invariance=not a.non_ti)
     dev = torch.device("cuda", 0)
     m = ops.GhmModel(T, a.L, a.s, a.q, p_y=np.ones(a.q) / a.q, device=dev)
+    m.set_gemm_mode({"f32": 0, "tf32": 1, "bf16": 2}[a.gemm])
     B, nL, q = a.B, m.n_leaves, a.q
     ldt = {"i64": torch.int64, "u8": torch.uint8, "none": None}[a.leaf]
     leaves = torch.empty((B, nL), dtype=ldt, device=dev) if ldt is not None else None
@@ -47,8 +49,9 @@ def main():
         fn = lambda i: ops.sample_into(m, B, ops.ROOT_UNIFORM, None, 100 + i, 0, root, leaves, post if bp else None, None)
         nbytes = B * (lsz * nL + 8 + (4 * q if bp else 0))
     else:
-        out = m.sample(B, seed=1, root_mode=ops.ROOT_UNIFORM, leaf_dtype=ldt or torch.int64, want_post=True, want_root_hd=True)
-        lv, ext = out["leaves"], out["root_hd"]
+        out = m.sample(B, seed=1, root_mode=ops.ROOT_UNIFORM, leaf_dtype=ldt or torch.int64)
+        lv = out["leaves"]
+        ext = m.bp_cls(lv)[1]
         z = m.gauss_noise(lv, a.sigma, seed=3)
         lb = lv.element_size()
         if a.op == "bp_cls":
@@ -77,7 +80,11 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         peak = 6650.0
-    print(json.dumps({"op": a.op, "L": a.L, "s": a.s, "q": a.q, "B": B, "leaf": a.leaf,
+    E_int = sum(a.s ** l for l in range(1, a.L))
+    E = E_int + nL
+    flops = {"bp_cls": 2.0 * q * q * E_int, "bp_dns": 4.0 * q * q * E}.get(a.op, 0.0) * B
+    print(json.dumps({"op": a.op, "L": a.L, "s": a.s, "q": a.q, "B": B, "leaf": a.leaf, "gemm": a.gemm,
+                      "gemm_tflops": round(flops / ms / 1e9, 2),
                       "ms": round(ms, 4), "trees_per_s": round(B / ms * 1e3), "GBps": round(nbytes / ms / 1e6, 1),
                       "hbm_frac": round(nbytes / ms / 1e6 / peak, 4)}))
 
