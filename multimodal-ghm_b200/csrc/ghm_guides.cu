@@ -12,6 +12,8 @@
 //   2. k_expand: a pure streaming kernel that broadcasts each depth-l node message over the
 //      s^(L-l) leaves below it and concatenates (hd | qd | bu): out[b][i][j*q+k] =
 //      SRC_j[b][node(l, i / s^(L-l))][k].  This is the HBM-write-bound part (13-71 KB per tree).
+#include <string.h>
+
 #include <algorithm>
 
 #include "ghm_vec.cuh"
@@ -215,56 +217,86 @@ __global__ void __launch_bounds__(GD_NT) k_lvl_dns(const GhmDev d, const LvlArgs
     }
 }
 
-// ---- expansion: node messages -> [B, n_L, C] guide tensor ------------------------------------------
-struct ExpandArgs {
-    int64_t B;
-    const float* src[3];     // up to 3 message arrays [B][n_nodes][q]
-    int nsrc;
-    int n_nodes, q, nL;
-    int node_off;            // first node of the level inside a tree
-    unsigned R_magic; int R; // leaves per node at this level: node = i / R
-    unsigned C_magic; int C; // C = nsrc * q
-    unsigned q_magic;
+// ---- expansion: node messages -> [B, n_L, C] guide tensors ------------------------------------------
+// ONE launch writes every tensor of a guide set (blockIdx.y = tensor).  A CTA streams whole tree rows: the
+// row of tree b in tensor t is n_L * C contiguous floats, written as consecutive 8-byte units by consecutive
+// lanes (fully coalesced); unit u = (leaf i, pair j) reads the float2 (k, k+1) of part j*2/q (hd | qd | bu)
+// of the depth-l ancestor of leaf i from the compact [B][node][q] store (L2 resident, 8-byte aligned for even q).
+#define EXP_MAX_T (2 * GHM_MAX_LEVELS + 1)
+struct ExpandT {
     float* out;              // [B][nL][C]
+    int level;               // depth of the broadcast nodes
+    int nsrc;                // C = nsrc * q
+    int src[3];              // index into ExpandAll::src for each part
+};
+struct ExpandAll {
+    int64_t B;
+    int n_t, n_nodes, q, nL, L;
+    int node_off[GHM_MAX_LEVELS + 1];
+    int R[GHM_MAX_LEVELS + 1]; unsigned R_magic[GHM_MAX_LEVELS + 1];      // leaves per depth-l node
+    const float* src[3];     // message arrays [B][n_nodes][q]
+    ExpandT t[EXP_MAX_T];
 };
 
 __device__ __forceinline__ int div_magic(int x, int div, unsigned magic) {
     return div == 1 ? x : (int)__umulhi((unsigned)x, magic);
 }
+static unsigned magic_of(int d) { return d >= 2 ? (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d) : 0u; }
 
-__global__ void __launch_bounds__(256) k_expand(const ExpandArgs a) {
-    const int row = a.nL * a.C;                          // floats per tree
-    for (int64_t b = blockIdx.y; b < a.B; b += gridDim.y) {
-        float* out = a.out + b * row;
-        for (int e = blockIdx.x * 256 + threadIdx.x; e < row; e += gridDim.x * 256) {
-            const int i = div_magic(e, a.C, a.C_magic);
-            const int c = e - i * a.C;
-            const int j = div_magic(c, a.q, a.q_magic);
-            const int k = c - j * a.q;
-            const int node = a.node_off + div_magic(i, a.R, a.R_magic);
-            const float* src = j == 0 ? a.src[0] : (j == 1 ? a.src[1] : a.src[2]);
-            out[e] = __ldg(src + (b * a.n_nodes + node) * a.q + k);
+template <bool VEC2>
+__global__ void __launch_bounds__(256) k_expand_all(const __grid_constant__ ExpandAll a) {
+    const ExpandT& t = a.t[blockIdx.y];
+    const int q = a.q, W = VEC2 ? 2 : 1;
+    const int hq = q / W;                                   // units per part
+    const int C2 = t.nsrc * hq;                             // units per leaf cell
+    const int upt = a.nL * C2;                              // units per tree row
+    const unsigned C2_magic = C2 >= 2 ? (unsigned)((0x100000000ull + (unsigned)C2 - 1) / (unsigned)C2) : 0u;
+    const unsigned hq_magic = hq >= 2 ? (unsigned)((0x100000000ull + (unsigned)hq - 1) / (unsigned)hq) : 0u;
+    const int R = a.R[t.level]; const unsigned Rm = a.R_magic[t.level];
+    const int noff = a.node_off[t.level];
+    const float* s0 = a.src[t.src[0]];
+    const float* s1 = a.src[t.src[t.nsrc > 1 ? 1 : 0]];
+    const float* s2 = a.src[t.src[t.nsrc > 2 ? 2 : 0]];
+    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
+        float* out = t.out + b * (int64_t)upt * W;
+        const int64_t sbase = b * (int64_t)a.n_nodes * q;
+        for (int u = threadIdx.x; u < upt; u += 256) {
+            const int i = div_magic(u, C2, C2_magic);
+            const int j = u - i * C2;
+            const int part = div_magic(j, hq, hq_magic);
+            const int kk = j - part * hq;
+            const int node = noff + div_magic(i, R, Rm);
+            const float* src = (part == 0 ? s0 : (part == 1 ? s1 : s2)) + sbase + (int64_t)node * q + kk * W;
+            if (VEC2) reinterpret_cast<float2*>(out)[u] = __ldg(reinterpret_cast<const float2*>(src));
+            else out[u] = __ldg(src);
         }
     }
 }
 
-static unsigned magic_of(int d) { return d >= 2 ? (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d) : 0u; }
-
-static int launch_expand(const GhmDev& d, int64_t B, int level, int n_nodes, bool all_levels, const float* s0,
-                         const float* s1, const float* s2, int nsrc, float* out, cudaStream_t st) {
-    ExpandArgs a{};
-    a.B = B; a.src[0] = s0; a.src[1] = s1; a.src[2] = s2; a.nsrc = nsrc;
-    a.n_nodes = n_nodes; a.q = d.q; a.nL = d.n_leaves;
-    a.node_off = level == 0 ? 0 : 1 + d.edge_off[level];
-    (void)all_levels;
-    a.R = d.spow[d.L - level]; a.R_magic = magic_of(a.R);
-    a.C = nsrc * d.q; a.C_magic = magic_of(a.C);
-    a.q_magic = magic_of(d.q);
-    a.out = out;
-    const int row = a.nL * a.C;
-    if ((int64_t)row * 1 >= (1ll << 31)) return ghm_fail(GHM_EUNSUP, "guide row too large");
-    dim3 grid((unsigned)std::min((row + 255) / 256, 64), (unsigned)std::min<int64_t>(B, 65535));
-    k_expand<<<grid, 256, 0, st>>>(a);
+// queue tensors into an ExpandAll, then one launch
+static void expand_setup(ExpandAll& a, const GhmDev& d, int64_t B, int n_nodes, const float* s0, const float* s1,
+                         const float* s2) {
+    memset(&a, 0, sizeof a);
+    a.B = B; a.n_nodes = n_nodes; a.q = d.q; a.nL = d.n_leaves; a.L = d.L;
+    a.src[0] = s0; a.src[1] = s1; a.src[2] = s2;
+    for (int l = 0; l <= d.L; ++l) {
+        a.node_off[l] = l == 0 ? 0 : 1 + d.edge_off[l];
+        a.R[l] = d.spow[d.L - l];
+        a.R_magic[l] = magic_of(a.R[l]);
+    }
+}
+static void expand_add(ExpandAll& a, float* out, int level, int nsrc, int p0, int p1, int p2) {
+    ExpandT& t = a.t[a.n_t++];
+    t.out = out; t.level = level; t.nsrc = nsrc; t.src[0] = p0; t.src[1] = p1; t.src[2] = p2;
+}
+static int expand_launch(const ExpandAll& a, cudaStream_t st) {
+    if (a.n_t == 0) return GHM_OK;
+    if ((int64_t)a.nL * 3 * a.q >= (1ll << 30)) return ghm_fail(GHM_EUNSUP, "guide row too large");
+    dim3 grid((unsigned)std::min<int64_t>(a.B, 148 * 32), (unsigned)a.n_t);
+    bool vec2 = (a.q % 2) == 0;
+    for (int i = 0; i < a.n_t; ++i) vec2 = vec2 && ((uintptr_t)a.t[i].out % 8) == 0;
+    for (int i = 0; i < 3; ++i) vec2 = vec2 && ((uintptr_t)a.src[i] % 8) == 0;
+    if (vec2) k_expand_all<true><<<grid, 256, 0, st>>>(a); else k_expand_all<false><<<grid, 256, 0, st>>>(a);
     GHM_CHECK_LAUNCH();
     return GHM_OK;
 }
@@ -325,21 +357,20 @@ extern "C" int ghm_guides_cls(const ghm_model_t* m, int64_t B, const void* leave
         return GHM_OK;
     });
     if (rc) return rc;
-    // guides[j] <- depth L-1-j, j = 0..L-2 read from HD (inside guides[L-1]); then the root level from root_hd
-    for (int j = 0; j < L - 1; ++j) {
-        rc = launch_expand(d, B, L - 1 - j, (int)n_int, false, HD, nullptr, nullptr, 1, guides[j], st);
+    // guides[j] <- depth L-1-j, j = 0..L-2, read from HD (inside guides[L-1]); then the root level from root_hd
+    {
+        ExpandAll e;
+        expand_setup(e, d, B, (int)n_int, HD, nullptr, nullptr);
+        for (int j = 0; j < L - 1; ++j) expand_add(e, guides[j], L - 1 - j, 1, 0, 0, 0);
+        rc = expand_launch(e, st);
         if (rc) return rc;
     }
-    // root level: source = root_hd viewed as [B][1 node][q]
-    {
-        ExpandArgs e{};
-        e.B = B; e.src[0] = root_hd; e.nsrc = 1; e.n_nodes = 1; e.q = d.q; e.nL = d.n_leaves; e.node_off = 0;
-        e.R = d.n_leaves; e.R_magic = magic_of(e.R); e.C = d.q; e.C_magic = magic_of(e.C); e.q_magic = magic_of(d.q);
-        e.out = guides[L - 1];
-        const int row = e.nL * e.C;
-        dim3 grid((unsigned)std::min((row + 255) / 256, 64), (unsigned)std::min<int64_t>(B, 65535));
-        k_expand<<<grid, 256, 0, st>>>(e);
-        GHM_CHECK_LAUNCH();
+    {   // root level: source = root_hd viewed as [B][1 node][q]
+        ExpandAll e;
+        expand_setup(e, d, B, 1, root_hd, nullptr, nullptr);
+        expand_add(e, guides[L - 1], 0, 1, 0, 0, 0);
+        rc = expand_launch(e, st);
+        if (rc) return rc;
     }
     return GHM_OK;
 }
@@ -372,16 +403,11 @@ extern "C" int ghm_guides_dns(const ghm_model_t* m, int64_t B, const float* z, f
         return GHM_OK;
     });
     if (rc || !guides) return rc;
-    // (hd|qd) depth L..1 ; root (hd|bu) ; (hd|qd|bu) depth 1..L      (reference :554-590)
-    for (int j = 0; j < L; ++j) {
-        rc = launch_expand(d, B, L - j, (int)nn, true, HD, QD, nullptr, 2, guides[j], st);
-        if (rc) return rc;
-    }
-    rc = launch_expand(d, B, 0, (int)nn, true, HD, BU, nullptr, 2, guides[L], st);
-    if (rc) return rc;
-    for (int j = 1; j <= L; ++j) {
-        rc = launch_expand(d, B, j, (int)nn, true, HD, QD, BU, 3, guides[L + j], st);
-        if (rc) return rc;
-    }
-    return GHM_OK;
+    // (hd|qd) depth L..1 ; root (hd|bu) ; (hd|qd|bu) depth 1..L      (reference :554-590) -- one launch
+    ExpandAll e;
+    expand_setup(e, d, B, (int)nn, HD, QD, BU);
+    for (int j = 0; j < L; ++j) expand_add(e, guides[j], L - j, 2, 0, 1, 0);
+    expand_add(e, guides[L], 0, 2, 0, 2, 0);
+    for (int j = 1; j <= L; ++j) expand_add(e, guides[L + j], j, 3, 0, 1, 2);
+    return expand_launch(e, st);
 }
