@@ -74,53 +74,66 @@ __device__ __forceinline__ int leaf_at(const void* leaves, int dtype, int64_t of
 // node id of (depth l, index idx) when depths 0..L are stored: off_all(l) = (s^l - 1)/(s - 1)
 __device__ __forceinline__ int node_off_all(const GhmDev& d, int l) { return l == 0 ? 0 : 1 + d.edge_off[l]; }
 
-// ---- BP_CLS, log domain (reference :185-221) ---------------------------------------------------
+// One THREAD per (tree, node) of one tree level, one launch per level: B * s^l threads, consecutive threads own
+// consecutive nodes of a tree, so the compact [B][node][q] message rows they read (children) and write are
+// adjacent 4q-byte rows (coalesced).  The level-serial, thread-per-tree form of round-1a left the SMs at 20 %
+// occupancy behind long dependent chains and was 3x slower than the expansion it feeds.
+struct LvlThread { int64_t b; int idx; bool ok; };
+__device__ __forceinline__ LvlThread lvl_thread(const GhmDev& d, int64_t B, int l) {
+    const int64_t t = (int64_t)blockIdx.x * GD_NT + threadIdx.x;
+    const int n = d.spow[l];
+    LvlThread r;
+    r.b = t / n;
+    r.idx = (int)(t - r.b * n);
+    r.ok = r.b < B;
+    return r;
+}
+static unsigned lvl_grid(const GhmDev& d, int64_t B, int l) { return (unsigned)((B * d.spow[l] + GD_NT - 1) / GD_NT); }
+
+// ---- BP_CLS, log domain (reference :185-221): nodes of depth l, bottom-up --------------------------
 template <int Q>
-__global__ void __launch_bounds__(GD_NT) k_lvl_cls(const GhmDev d, const LvlArgs a) {
-    const int64_t b = (int64_t)blockIdx.x * GD_NT + threadIdx.x;
-    if (b >= a.B) return;
-    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves;
+__global__ void __launch_bounds__(GD_NT) k_lvl_cls(const GhmDev d, const LvlArgs a, int l) {
+    const LvlThread th = lvl_thread(d, a.B, l);
+    if (!th.ok) return;
+    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves, idx = th.idx;
+    const int64_t b = th.b;
     float* HD = a.HD + b * (int64_t)a.n_nodes * q;
     float acc[Q];
-    for (int l = L - 1; l >= 0; --l) {
-        const int n = d.spow[l];
-        for (int idx = 0; idx < n; ++idx) {
 #pragma unroll
-            for (int k = 0; k < Q; ++k) acc[k] = (k < q) ? 0.f : -INFINITY;
-            for (int c = 0; c < s; ++c) {
-                const int child = idx * s + c;
-                const int mi = d.mat_off[l + 1] + (d.ti ? c : child);
-                if (l == L - 1) {
-                    const int x = leaf_at(a.leaves, a.leaf_dtype, b * nL + child, q, d.status);
-                    const float* row = d.TlogT + ((size_t)mi * Q + x) * Q;          // log T[:, x]   (:196)
+    for (int k = 0; k < Q; ++k) acc[k] = (k < q) ? 0.f : -INFINITY;
+    for (int c = 0; c < s; ++c) {
+        const int child = idx * s + c;
+        const int mi = d.mat_off[l + 1] + (d.ti ? c : child);
+        if (l == L - 1) {
+            const int x = leaf_at(a.leaves, a.leaf_dtype, b * nL + child, q, d.status);
+            const float* row = d.TlogT + ((size_t)mi * Q + x) * Q;          // log T[:, x]   (:196)
 #pragma unroll
-                    for (int k = 0; k < Q; ++k)
-                        if (k < q) acc[k] += __ldg(row + k);
-                } else {
-                    float h[Q], m[Q];
-                    load_vec<Q>(HD + (int64_t)(node_off_all(d, l + 1) + child) * q, h, q);
-                    log_matvec<Q>(d.Tlin + (size_t)mi * Q * Q, h, m, q);             // log(T @ exp(hd))  (:207)
+            for (int k = 0; k < Q; ++k)
+                if (k < q) acc[k] += __ldg(row + k);
+        } else {
+            float h[Q], m[Q];
+            load_vec<Q>(HD + (int64_t)(node_off_all(d, l + 1) + child) * q, h, q);
+            log_matvec<Q>(d.Tlin + (size_t)mi * Q * Q, h, m, q);             // log(T @ exp(hd))  (:207)
 #pragma unroll
-                    for (int k = 0; k < Q; ++k)
-                        if (k < q) acc[k] += m[k];
-                }
-            }
-            const float mx = ghm_vmax<Q>(acc);
-#pragma unroll
-            for (int k = 0; k < Q; ++k) acc[k] -= mx;                                 // (:197,208)
-            store_vec<Q>(HD + (int64_t)(node_off_all(d, l) + idx) * q, acc, q);
+            for (int k = 0; k < Q; ++k)
+                if (k < q) acc[k] += m[k];
         }
     }
+    const float mx = ghm_vmax<Q>(acc);
+#pragma unroll
+    for (int k = 0; k < Q; ++k) acc[k] -= mx;                                 // (:197,208)
+    store_vec<Q>(HD + (int64_t)(node_off_all(d, l) + idx) * q, acc, q);
+    if (l > 0) return;
     // root: acc == hd(root)
     if (a.root_hd) store_vec<Q>(a.root_hd + b * q, acc, q);
     if (a.post) {
         float h0[Q];
 #pragma unroll
         for (int k = 0; k < Q; ++k) h0[k] = (k < q) ? acc[k] + logf(__ldg(d.py + k)) : -INFINITY;   // (:213)
-        const float mx = ghm_vmax<Q>(h0);
+        const float m0 = ghm_vmax<Q>(h0);
         float sum = 0.f;
 #pragma unroll
-        for (int k = 0; k < Q; ++k) { h0[k] = (k < q) ? expf(h0[k] - mx) : 0.f; sum += h0[k]; }
+        for (int k = 0; k < Q; ++k) { h0[k] = (k < q) ? expf(h0[k] - m0) : 0.f; sum += h0[k]; }
         const float inv = 1.0f / sum;
 #pragma unroll
         for (int k = 0; k < Q; ++k) h0[k] *= inv;
@@ -128,56 +141,44 @@ __global__ void __launch_bounds__(GD_NT) k_lvl_cls(const GhmDev d, const LvlArgs
     }
 }
 
-// ---- BP_DNS, log domain (reference :467-523) ---------------------------------------------------
+// ---- BP_DNS, log domain (reference :467-523): upward pass, nodes of depth l ------------------------
 template <int Q>
-__global__ void __launch_bounds__(GD_NT) k_lvl_dns(const GhmDev d, const LvlArgs a) {
-    const int64_t b = (int64_t)blockIdx.x * GD_NT + threadIdx.x;
-    if (b >= a.B) return;
-    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves;
+__global__ void __launch_bounds__(GD_NT) k_lvl_dns_up(const GhmDev d, const LvlArgs a, int l) {
+    const LvlThread th = lvl_thread(d, a.B, l);
+    if (!th.ok) return;
+    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves, idx = th.idx;
+    const int64_t b = th.b;
     const int64_t base = b * (int64_t)a.n_nodes * q;
     float* HD = a.HD + base;
     float* QD = a.QD + base;
-    float* BU = a.BU + base;
-    const float inv2s2 = 0.5f / (a.sigma * a.sigma);
-    // leaves: hd unshifted (:485), qd = log(T @ exp(hd)) (:487)
-    {
-        const int o = node_off_all(d, L);
-        for (int i = 0; i < nL; ++i) {
-            const float zi = a.z[b * nL + i];
-            float h[Q], m[Q];
-#pragma unroll
-            for (int k = 0; k < Q; ++k) { const float dlt = zi - (float)k; h[k] = (k < q) ? -dlt * dlt * inv2s2 : -INFINITY; }
-            const int mi = d.mat_off[L] + (d.ti ? i % s : i);
-            log_matvec<Q>(d.Tlin + (size_t)mi * Q * Q, h, m, q);
-            store_vec<Q>(HD + (int64_t)(o + i) * q, h, q);
-            store_vec<Q>(QD + (int64_t)(o + i) * q, m, q);
-        }
-    }
-    // internal nodes bottom-up: hd = sum qd(children) - max (:494-496), qd = log(T @ exp(hd)) (:497)
+    const int node = node_off_all(d, l) + idx;
     float acc[Q];
-    for (int l = L - 1; l >= 0; --l) {
-        const int n = d.spow[l];
-        for (int idx = 0; idx < n; ++idx) {
+    if (l == L) {                                             // leaves: hd unshifted (:485), qd = log(T @ exp(hd)) (:487)
+        const float inv2s2 = 0.5f / (a.sigma * a.sigma);
+        const float zi = a.z[b * nL + idx];
 #pragma unroll
-            for (int k = 0; k < Q; ++k) acc[k] = (k < q) ? 0.f : -INFINITY;
-            for (int c = 0; c < s; ++c) {
-                float m[Q];
-                load_vec<Q>(QD + (int64_t)(node_off_all(d, l + 1) + idx * s + c) * q, m, q);
+        for (int k = 0; k < Q; ++k) { const float dlt = zi - (float)k; acc[k] = (k < q) ? -dlt * dlt * inv2s2 : -INFINITY; }
+    } else {                                                  // hd = sum qd(children) - max (:494-496)
 #pragma unroll
-                for (int k = 0; k < Q; ++k)
-                    if (k < q) acc[k] += m[k];
-            }
-            const float mx = ghm_vmax<Q>(acc);
+        for (int k = 0; k < Q; ++k) acc[k] = (k < q) ? 0.f : -INFINITY;
+        for (int c = 0; c < s; ++c) {
+            float m[Q];
+            load_vec<Q>(QD + (int64_t)(node_off_all(d, l + 1) + idx * s + c) * q, m, q);
 #pragma unroll
-            for (int k = 0; k < Q; ++k) acc[k] -= mx;
-            if (l > 0) {
-                const int mi = d.mat_off[l] + (d.ti ? idx % s : idx);
-                float m[Q];
-                log_matvec<Q>(d.Tlin + (size_t)mi * Q * Q, acc, m, q);
-                store_vec<Q>(HD + (int64_t)(node_off_all(d, l) + idx) * q, acc, q);
-                store_vec<Q>(QD + (int64_t)(node_off_all(d, l) + idx) * q, m, q);
-            }
+            for (int k = 0; k < Q; ++k)
+                if (k < q) acc[k] += m[k];
         }
+        const float mx = ghm_vmax<Q>(acc);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) acc[k] -= mx;
+    }
+    if (l > 0) {
+        const int mi = d.mat_off[l] + (d.ti ? idx - ghm_div_s(idx, d) * s : idx);
+        float m[Q];
+        log_matvec<Q>(d.Tlin + (size_t)mi * Q * Q, acc, m, q);                // qd = log(T @ exp(hd)) (:497)
+        store_vec<Q>(HD + (int64_t)node * q, acc, q);
+        store_vec<Q>(QD + (int64_t)node * q, m, q);
+        return;
     }
     // root: bu aliases hd and gets the external message without a re-shift (:501-506)
     if (a.ext) {
@@ -186,34 +187,39 @@ __global__ void __launch_bounds__(GD_NT) k_lvl_dns(const GhmDev d, const LvlArgs
             if (k < q) acc[k] += a.ext[b * q + k];
     }
     store_vec<Q>(HD, acc, q);
-    store_vec<Q>(BU, acc, q);
-    // top-down: bu = hd + log(T^T @ exp(bu_parent - qd)) - max (:509-514)
-    for (int l = 1; l <= L; ++l) {
-        const int n = d.spow[l];
-        for (int idx = 0; idx < n; ++idx) {
-            const int node = node_off_all(d, l) + idx;
-            const int par = node_off_all(d, l - 1) + ghm_div_s(idx, d);
-            float bp[Q], qv[Q], hv[Q], m[Q];
-            load_vec<Q>(BU + (int64_t)par * q, bp, q);
-            load_vec<Q>(QD + (int64_t)node * q, qv, q);
-            load_vec<Q>(HD + (int64_t)node * q, hv, q);
+    store_vec<Q>(a.BU + base, acc, q);
+}
+
+// ---- BP_DNS downward pass: bu = hd + log(T^T @ exp(bu_parent - qd)) - max (:509-514), nodes of depth l >= 1 ----
+template <int Q>
+__global__ void __launch_bounds__(GD_NT) k_lvl_dns_down(const GhmDev d, const LvlArgs a, int l) {
+    const LvlThread th = lvl_thread(d, a.B, l);
+    if (!th.ok) return;
+    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves, idx = th.idx;
+    const int64_t b = th.b;
+    const int64_t base = b * (int64_t)a.n_nodes * q;
+    const int node = node_off_all(d, l) + idx;
+    const int pidx = ghm_div_s(idx, d);
+    const int par = node_off_all(d, l - 1) + pidx;
+    float bp[Q], qv[Q], hv[Q], m[Q];
+    load_vec<Q>(a.BU + base + (int64_t)par * q, bp, q);
+    load_vec<Q>(a.QD + base + (int64_t)node * q, qv, q);
+    load_vec<Q>(a.HD + base + (int64_t)node * q, hv, q);
 #pragma unroll
-            for (int k = 0; k < Q; ++k) bp[k] = (k < q) ? bp[k] - qv[k] : -INFINITY;
-            const int mi = d.mat_off[l] + (d.ti ? idx % s : idx);
-            log_matvec_t<Q>(d.Tlin + (size_t)mi * Q * Q, bp, m, q);
+    for (int k = 0; k < Q; ++k) bp[k] = (k < q) ? bp[k] - qv[k] : -INFINITY;
+    const int mi = d.mat_off[l] + (d.ti ? idx - pidx * s : idx);
+    log_matvec_t<Q>(d.Tlin + (size_t)mi * Q * Q, bp, m, q);
 #pragma unroll
-            for (int k = 0; k < Q; ++k) m[k] = (k < q) ? hv[k] + m[k] : -INFINITY;
-            const float mx = ghm_vmax<Q>(m);
+    for (int k = 0; k < Q; ++k) m[k] = (k < q) ? hv[k] + m[k] : -INFINITY;
+    const float mx = ghm_vmax<Q>(m);
 #pragma unroll
-            for (int k = 0; k < Q; ++k) m[k] -= mx;
-            store_vec<Q>(BU + (int64_t)node * q, m, q);
-            if (l == L && a.mean) {                                               // (:516-519)
-                float num = 0.f, den = 0.f;
+    for (int k = 0; k < Q; ++k) m[k] -= mx;
+    store_vec<Q>(a.BU + base + (int64_t)node * q, m, q);
+    if (l == L && a.mean) {                                                   // (:516-519)
+        float num = 0.f, den = 0.f;
 #pragma unroll
-                for (int k = 0; k < Q; ++k) { const float e = (k < q) ? expf(m[k]) : 0.f; num += (float)k * e; den += e; }
-                a.mean[b * nL + idx] = num / den;
-            }
-        }
+        for (int k = 0; k < Q; ++k) { const float e = (k < q) ? expf(m[k]) : 0.f; num += (float)k * e; den += e; }
+        a.mean[b * nL + idx] = num / den;
     }
 }
 
@@ -352,8 +358,10 @@ extern "C" int ghm_guides_cls(const ghm_model_t* m, int64_t B, const void* leave
     if (!root_hd) return ghm_fail(GHM_EINVAL, "ghm_guides_cls: root_hd output is required");
     int rc = dispatch_q(d.q, [&](auto Qc) -> int {
         constexpr int Q = decltype(Qc)::value;
-        k_lvl_cls<Q><<<(unsigned)((B + GD_NT - 1) / GD_NT), GD_NT, 0, st>>>(d, a);
-        GHM_CHECK_LAUNCH();
+        for (int l = d.L - 1; l >= 0; --l) {
+            k_lvl_cls<Q><<<lvl_grid(d, B, l), GD_NT, 0, st>>>(d, a, l);
+            GHM_CHECK_LAUNCH();
+        }
         return GHM_OK;
     });
     if (rc) return rc;
@@ -398,8 +406,14 @@ extern "C" int ghm_guides_dns(const ghm_model_t* m, int64_t B, const float* z, f
     a.B = B; a.z = z; a.sigma = sigma; a.ext = ext; a.HD = HD; a.QD = QD; a.BU = BU; a.n_nodes = (int)nn; a.mean = mean;
     int rc = dispatch_q(d.q, [&](auto Qc) -> int {
         constexpr int Q = decltype(Qc)::value;
-        k_lvl_dns<Q><<<(unsigned)((B + GD_NT - 1) / GD_NT), GD_NT, 0, st>>>(d, a);
-        GHM_CHECK_LAUNCH();
+        for (int l = d.L; l >= 0; --l) {
+            k_lvl_dns_up<Q><<<lvl_grid(d, B, l), GD_NT, 0, st>>>(d, a, l);
+            GHM_CHECK_LAUNCH();
+        }
+        for (int l = 1; l <= d.L; ++l) {
+            k_lvl_dns_down<Q><<<lvl_grid(d, B, l), GD_NT, 0, st>>>(d, a, l);
+            GHM_CHECK_LAUNCH();
+        }
         return GHM_OK;
     });
     if (rc || !guides) return rc;
