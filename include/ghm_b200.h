@@ -54,6 +54,7 @@ extern "C" {
 #define GHM_ROOT_GIVEN    0   /* root_in supplied  (reference GHMTree(root=...), :153-156) */
 #define GHM_ROOT_PRIOR    1   /* draw from the model prior p_y (:158) */
 #define GHM_ROOT_UNIFORM  2   /* np.random.choice(q,size=B): uniform, ignores p_y (:674,758,858,906) */
+#define GHM_ROOT_SHARED   3   /* (ghm_sample_paired) uniform roots re-drawn from the PARTNER modality's Philox key */
 
 typedef struct ghm_model ghm_model_t;   /* opaque; owns only the device-side tables */
 
@@ -108,6 +109,14 @@ GHM_API int ghm_sample(const ghm_model_t* m, int64_t B, int root_mode, const int
 GHM_API int ghm_sample_mixed(const ghm_model_t* m, int64_t B, int64_t n_given, const int64_t* root_in,
                      uint64_t seed, uint64_t tree_offset, int64_t* root_out, void* leaves_out, int leaf_dtype,
                      float* post_out, float* root_hd_out, void* stream);
+
+/* The image side of a text/image pair WITHOUT a dependency on the text launch (:858-861, :759-760): trees
+ * [0, n_shared) re-draw the uniform root the partner modality drew (Philox key `root_seed` = the partner's seed,
+ * same global tree index), trees [n_shared, B) draw their own uniform roots.  The two modalities can then be
+ * launched on different streams and their CTAs fill each other's tail waves.  Philox mode only. */
+GHM_API int ghm_sample_paired(const ghm_model_t* m, int64_t B, int64_t n_shared, uint64_t root_seed, uint64_t seed,
+                      uint64_t tree_offset, int64_t* root_out, void* leaves_out, int leaf_dtype,
+                      float* post_out, float* root_hd_out, void* stream);
 
 /* ---- K2: root posterior  (GHMTree.BP_CLS, :185-221) ----------------------------
  *   post     : f32 [B, q]  p(root | leaves)               (posterior_probability_CLS^T)

@@ -57,14 +57,20 @@ extern "C" int ghm_host_clip_bayes(const ghm_model_t* text_c, const ghm_model_t*
     cudaStream_t st = text->stream;
 
     GHM_CUDA_TRY(cudaMemsetAsync(d_sums, 0, 3 * sizeof(double), st));
-    // text: B trees, uniform roots (:758)
+    // text: B trees, uniform roots (:758) on the text model's stream; image: the first 2n trees re-draw the text roots
+    // from the text key, the other (K-1)n draw fresh uniform roots (:759-760) -- independent of the text launch, so it
+    // runs concurrently on the image model's stream and the two kernels fill each other's tail waves
+    const uint64_t iseed = seed ^ GHM_IMAGE_SEED_XOR;
+    cudaStream_t st2 = image->stream;
+    GHM_CUDA_TRY(cudaEventRecord(text->upload_done, st));              // (re-used as a plain ordering event)
+    GHM_CUDA_TRY(cudaStreamWaitEvent(st2, text->upload_done, 0));
+    rc = ghm_sample_paired(image, B, 2 * n, seed, iseed, tree_offset, nullptr, d_il, leaf_dtype, d_ipp, nullptr, st2);
+    if (rc) return rc;
     rc = ghm_sample(text, B, GHM_ROOT_UNIFORM, nullptr, nullptr, seed, tree_offset, d_root, d_tl, leaf_dtype, d_tpp,
                     nullptr, st);
     if (rc) return rc;
-    // image: first 2n trees share the text roots, the other (K-1)n draw fresh uniform roots (:759-760)
-    const uint64_t iseed = seed ^ GHM_IMAGE_SEED_XOR;
-    rc = ghm_sample_mixed(image, B, 2 * n, d_root, iseed, tree_offset, nullptr, d_il, leaf_dtype, d_ipp, nullptr, st);
-    if (rc) return rc;
+    GHM_CUDA_TRY(cudaEventRecord(image->upload_done, st2));
+    GHM_CUDA_TRY(cudaStreamWaitEvent(st, image->upload_done, 0));
     rc = ghm_risk_clip(d_tpp, d_ipp, n, K, q, 0, n, d_sums, st);
     if (rc) return rc;
     GHM_CUDA_TRY(cudaMemcpyAsync(sums_host, d_sums, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -89,11 +89,11 @@ struct DeviceGuard {
 };
 
 static int sample_common(const ghm_model_t* m, int64_t B, int root_mode, int64_t n_given, const int64_t* root_in,
-                         const double* U, uint64_t seed, uint64_t tree_offset, int64_t* root_out, void* leaves_out,
+                         uint64_t root_seed, const double* U, uint64_t seed, uint64_t tree_offset, int64_t* root_out, void* leaves_out,
                          int leaf_dtype, float* post_out, float* root_hd_out, void* stream) {
     if (!m) return ghm_fail(GHM_EINVAL, "ghm_sample: null model");
     if (B <= 0) return B == 0 ? GHM_OK : ghm_fail(GHM_EINVAL, "ghm_sample: negative batch");
-    if (root_mode < 0 || root_mode > 2) return ghm_fail(GHM_EINVAL, "ghm_sample: bad root_mode %d", root_mode);
+    if (root_mode < 0 || root_mode > 3) return ghm_fail(GHM_EINVAL, "ghm_sample: bad root_mode %d", root_mode);
     if (root_mode == GHM_ROOT_GIVEN && n_given > 0 && !root_in) return ghm_fail(GHM_EINVAL, "ghm_sample: root_in is null");
     if (n_given < 0 || n_given > B) return ghm_fail(GHM_EINVAL, "ghm_sample: n_given outside [0, B]");
     if (U && (root_mode != GHM_ROOT_GIVEN || n_given != B))
@@ -101,7 +101,8 @@ static int sample_common(const ghm_model_t* m, int64_t B, int root_mode, int64_t
     if (leaf_dtype != GHM_LEAF_I64 && leaf_dtype != GHM_LEAF_U8) return ghm_fail(GHM_EINVAL, "bad leaf_dtype %d", leaf_dtype);
     DeviceGuard g(m->device);
     TreeArgs a{};
-    a.B = B; a.root_mode = root_mode; a.n_given = n_given; a.root_in = root_in; a.U = U; a.seed = seed;
+    a.B = B; a.root_mode = root_mode; a.n_given = n_given; a.root_in = root_in; a.root_seed = root_seed; a.U = U;
+    a.seed = seed;
     a.tree_offset = tree_offset;
     a.root_out = root_out; a.leaves = leaves_out; a.leaf_dtype = leaf_dtype; a.post = post_out; a.root_hd = root_hd_out;
     const bool bp = post_out || root_hd_out;
@@ -122,15 +123,23 @@ static int sample_common(const ghm_model_t* m, int64_t B, int root_mode, int64_t
 extern "C" int ghm_sample(const ghm_model_t* m, int64_t B, int root_mode, const int64_t* root_in, const double* U,
                           uint64_t seed, uint64_t tree_offset, int64_t* root_out, void* leaves_out, int leaf_dtype,
                           float* post_out, float* root_hd_out, void* stream) {
-    return sample_common(m, B, root_mode, root_mode == GHM_ROOT_GIVEN ? B : 0, root_in, U, seed, tree_offset, root_out,
+    if (root_mode == GHM_ROOT_SHARED) return ghm_fail(GHM_EINVAL, "ghm_sample: GHM_ROOT_SHARED is ghm_sample_paired's mode");
+    return sample_common(m, B, root_mode, root_mode == GHM_ROOT_GIVEN ? B : 0, root_in, 0, U, seed, tree_offset, root_out,
                          leaves_out, leaf_dtype, post_out, root_hd_out, stream);
 }
 
 extern "C" int ghm_sample_mixed(const ghm_model_t* m, int64_t B, int64_t n_given, const int64_t* root_in, uint64_t seed,
                                 uint64_t tree_offset, int64_t* root_out, void* leaves_out, int leaf_dtype,
                                 float* post_out, float* root_hd_out, void* stream) {
-    return sample_common(m, B, GHM_ROOT_GIVEN, n_given, root_in, nullptr, seed, tree_offset, root_out, leaves_out,
+    return sample_common(m, B, GHM_ROOT_GIVEN, n_given, root_in, 0, nullptr, seed, tree_offset, root_out, leaves_out,
                          leaf_dtype, post_out, root_hd_out, stream);
+}
+
+extern "C" int ghm_sample_paired(const ghm_model_t* m, int64_t B, int64_t n_shared, uint64_t root_seed, uint64_t seed,
+                                 uint64_t tree_offset, int64_t* root_out, void* leaves_out, int leaf_dtype,
+                                 float* post_out, float* root_hd_out, void* stream) {
+    return sample_common(m, B, GHM_ROOT_SHARED, n_shared, nullptr, root_seed, nullptr, seed, tree_offset, root_out,
+                         leaves_out, leaf_dtype, post_out, root_hd_out, stream);
 }
 
 extern "C" int64_t ghm_bp_cls_workspace_bytes(const ghm_model_t* m, int64_t B) {

@@ -49,6 +49,7 @@ struct TreeArgs {
     int root_mode;
     int64_t n_given;       // GHM_ROOT_GIVEN: trees [0, n_given) take root_in, the rest draw uniform roots (ClipSampler image layout)
     const int64_t* root_in;
+    uint64_t root_seed;    // GHM_ROOT_SHARED: Philox key of the roots of trees [0, n_given) (the partner modality's seed)
     const double* U;
     uint64_t seed, tree_offset;
     int64_t* root_out;
@@ -279,7 +280,8 @@ k_tree2(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a, co
                 if (r < 0 || r >= q) { atomicOr(d.status, 1); r = r < 0 ? 0 : q - 1; }
                 x0 = (int)r;
             } else {
-                const uint4 rb = ghm_rng_block(a.seed, tree[t], 0u, 0u, GHM_STREAM_TREE);
+                const bool shared = a.root_mode == GHM_ROOT_SHARED && (active[t] ? bt[t] : a.B - 1) < a.n_given;
+                const uint4 rb = ghm_rng_block(shared ? a.root_seed : a.seed, tree[t], 0u, 0u, GHM_STREAM_TREE);
                 const uint32_t* rc = a.root_mode == GHM_ROOT_PRIOR ? d.root_cdfu_prior : d.root_cdfu_unif;
                 int cnt = 0;
                 for (int k = 0; k < q - 1; ++k) cnt += (rb.x >= __ldg(rc + k)) ? 1 : 0;

@@ -365,6 +365,12 @@ class _SamplerBase:
         self.rng, self.seed = rng, int(seed)
         self.tree_offset = 0          # global index of the next Philox tree (explicit, resumable RNG state)
 
+    def _side_stream(self):
+        st = getattr(self, "_side", None)
+        if st is None:
+            st = self._side = torch.cuda.Stream(device=self.device)
+        return st
+
     def _advance(self, n):
         off = self.tree_offset
         self.tree_offset += int(n)
@@ -609,8 +615,15 @@ class ClipSampler(DoubleSampler):
                  "root": torch.empty(B, dtype=torch.int64, device=dev),
                  "post": torch.empty((B, q), dtype=torch.float32, device=dev) if want_post else None}
             iseed = self.seed ^ ops.IMAGE_SEED_XOR
+            # The image side re-draws the shared roots from the text key (ghm_sample_paired), so the two launches are
+            # independent: they go to two streams and their CTAs fill each other's tail waves.
+            cur = torch.cuda.current_stream(dev)
+            side = self._side_stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                ops.sample_paired_into(self.i_model, B, 2 * n, self.seed, iseed, off, i["root"], i["leaves"], i["post"], None)
             ops.sample_into(self.t_model, B, ops.ROOT_UNIFORM, None, self.seed, off, t["root"], t["leaves"], t["post"], None)
-            ops.sample_mixed_into(self.i_model, B, 2 * n, t["root"], iseed, off, i["root"], i["leaves"], i["post"], None)
+            cur.wait_stream(side)
             return {"t": t, "i": i, "n_local": n}
         Bl = nl * (K + 1)
         t = {"leaves": torch.empty((Bl, self.t_model.n_leaves), dtype=torch.int64, device=dev) if want_leaves else None,

@@ -282,6 +282,18 @@ def sample_mixed_into(model, batch, n_given, root_in, seed, tree_offset, root_ou
                                           _ptr(post_out), _ptr(root_hd_out), _stream()))
 
 
+def sample_paired_into(model, batch, n_shared, root_seed, seed, tree_offset, root_out, leaves_out, post_out, root_hd_out):
+    """ghm_sample_paired: trees [0, n_shared) re-draw the partner modality's uniform root (Philox key ``root_seed``),
+    the rest draw their own; no dependency on the partner's launch, so the two may run on different streams."""
+    for t in (root_out, leaves_out, post_out, root_hd_out):
+        assert t is None or t.is_contiguous()
+    with torch.cuda.device(model.device):
+        check(model._lib.ghm_sample_paired(model._h, int(batch), int(n_shared), root_seed, seed, tree_offset,
+                                           _ptr(root_out), _ptr(leaves_out),
+                                           _leaf_code(leaves_out) if leaves_out is not None else LEAF_I64,
+                                           _ptr(post_out), _ptr(root_hd_out), _stream()))
+
+
 def new_sums(device):
     """Zeroed {sum, sum of squares, count} accumulator (float64[3]) for the risk kernels."""
     return torch.zeros(3, dtype=torch.float64, device=device)

@@ -201,3 +201,24 @@ def test_leaf_dtype_alignment_and_tpt_variants_agree(ops, L, s, q):
     np.testing.assert_allclose(p4.cpu().numpy(), ref["post"].cpu().numpy(), rtol=RTOL, atol=1e-7)
     np.testing.assert_allclose(h4.cpu().numpy(), ref["root_hd"].cpu().numpy(), rtol=RTOL, atol=2e-5)
     assert m.status() == 0
+
+
+def test_paired_sampling_redraws_partner_roots(ops):
+    """ghm_sample_paired: the image launch re-draws the text roots from the text Philox key -- same trees as feeding the
+    text launch's roots in (ghm_sample_mixed), without depending on the text launch."""
+    from oracle import ghm_oracle as O
+    u = np.ones(10) / 10
+    mo = O.PairedModel([4, 3], [3, 3], [u, u], [.2, .3])
+    tm = ops.GhmModel(mo.t_T, 4, 3, 10, device="cuda:0")
+    im = ops.GhmModel(mo.i_T, 3, 3, 10, device="cuda:0")
+    B, n_shared, seed, iseed, off = 1000, 400, 77, 77 ^ ops.IMAGE_SEED_XOR, 12345
+    t = tm.sample(B, seed=seed, tree_offset=off, root_mode=ops.ROOT_UNIFORM)
+    ref_l = torch.empty((B, 27), dtype=torch.int64, device="cuda:0")
+    ref_r = torch.empty(B, dtype=torch.int64, device="cuda:0")
+    ref_p = torch.empty((B, 10), dtype=torch.float32, device="cuda:0")
+    ops.sample_mixed_into(im, B, n_shared, t["root"], iseed, off, ref_r, ref_l, ref_p, None)
+    got_l, got_r, got_p = torch.empty_like(ref_l), torch.empty_like(ref_r), torch.empty_like(ref_p)
+    ops.sample_paired_into(im, B, n_shared, seed, iseed, off, got_r, got_l, got_p, None)
+    assert torch.equal(got_r, ref_r) and torch.equal(got_l, ref_l) and torch.equal(got_p, ref_p)
+    assert torch.equal(got_r[:n_shared], t["root"][:n_shared])
+    assert not torch.equal(got_r[n_shared:], t["root"][n_shared:])
