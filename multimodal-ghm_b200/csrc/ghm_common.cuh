@@ -55,6 +55,8 @@ struct ghm_model {
     int gemm_mode;       // GHM_GEMM_*: arithmetic of the wide path's row-GEMMs
     void* h_slab;        // pinned host image of the slab (table derivation target, source of H2D uploads)
     float* h_TTp;        // -> TTp inside h_slab (source of the constant-bank kernel parameter)
+    float* h_Tlin;       // -> Tlin / TlinT inside h_slab (constant-bank parameter of k_dns2)
+    float* h_TlinT;
     cudaEvent_t upload_done;
     void* slab;          // single device allocation holding every table
     size_t slab_bytes;

@@ -212,6 +212,8 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     d.root_cdfu_unif = (const uint32_t*)(base + o.rcu);
     d.status = (int*)(base + o.status);
     m->h_TTp = (float*)((char*)m->h_slab + o.TTp);
+    m->h_Tlin = (float*)((char*)m->h_slab + o.Tlin);
+    m->h_TlinT = (float*)((char*)m->h_slab + o.TlinT);
     *out = m;
     return GHM_OK;
 }
