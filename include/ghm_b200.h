@@ -173,6 +173,12 @@ GHM_API int ghm_risk_ce(const float* pp, const void* target, int leaf_dtype, int
                 int64_t target_stride, int64_t target_offset, int64_t row_group,
                 double* sums, void* stream);
 
+/* zero-shot classification risk (figures/eval-zsc-risk.py:66-83): the image root posterior i_pp f32 [B, q] is pushed
+ * down the leftmost path of the TEXT tree (x <- x @ T_l[0], every level) and scored against the first text leaf:
+ * accumulates -log x[t_leaves[b, 0]] into sums[3]. */
+GHM_API int ghm_risk_zsc(const ghm_model_t* text, int64_t B, const float* i_pp, const void* t_leaves, int leaf_dtype,
+                 double* sums, void* stream);
+
 /* ---- Gaussian observations  (image_tree_noise, :733,:867) -----------------------
  * z[b,i] = leaves[b,i] + sigma * N(0,1), Philox stream 1 keyed like ghm_sample. */
 GHM_API int ghm_gauss_noise(const ghm_model_t* m, int64_t B, const void* leaves, int leaf_dtype, float sigma,

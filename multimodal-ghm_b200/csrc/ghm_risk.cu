@@ -11,7 +11,7 @@
 // reference's dense ((K-1)n x n) 0/1 matmul (:26-27, O(n^2) memory) is a K-1 term segmented sum here.
 #include <algorithm>
 
-#include "ghm_common.cuh"
+#include "ghm_vec.cuh"
 
 #define RISK_NT 256
 
@@ -149,6 +149,61 @@ extern "C" int ghm_risk_ce(const float* pp, const void* target, int leaf_dtype, 
                                                                        t_off, row_group, sums);
     else
         return ghm_fail(GHM_EINVAL, "bad leaf_dtype %d", leaf_dtype);
+    GHM_CHECK_LAUNCH();
+    return GHM_OK;
+}
+
+// ---- zero-shot classification risk (figures/eval-zsc-risk.py:66-83, eval-zsc-ood.py:23-28) ---------------
+// The image-side root posterior is pushed down the LEFTMOST path of the text tree, x <- x @ T_l[0] for every level,
+// which is the Bayes predictive distribution of the first text leaf given the image; loss = -log x[first text leaf].
+template <int Q, typename LeafT>
+__global__ void __launch_bounds__(RISK_NT) k_risk_zsc(const GhmDev d, const float* __restrict__ i_pp,
+                                                      const LeafT* __restrict__ t_leaves, int64_t B, double* sums) {
+    const int q = d.q;
+    double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+    for (int64_t b = (int64_t)blockIdx.x * RISK_NT + threadIdx.x; b < B; b += (int64_t)gridDim.x * RISK_NT) {
+        float v[Q], w[Q];
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v[k] = (k < q) ? i_pp[b * q + k] : 0.f;
+        for (int l = 1; l <= d.L; ++l) {
+            ghm_matvec_t<Q>(d.Tlin + (size_t)d.mat_off[l] * Q * Q, v, w);       // edge into node 0 of depth l
+#pragma unroll
+            for (int k = 0; k < Q; ++k) v[k] = w[k];
+        }
+        int64_t y = (int64_t)t_leaves[b * d.n_leaves];
+        y = y < 0 ? 0 : (y >= q ? q - 1 : y);
+        float vy = 0.f;
+#pragma unroll
+        for (int k = 0; k < Q; ++k) vy = (k == (int)y) ? v[k] : vy;
+        const double l = -(double)logf(vy);                  // float32 log like the reference's torch path
+        s1 += l; s2 += l * l; cnt += 1.0;
+    }
+    block_accumulate(s1, s2, cnt, sums);
+}
+
+extern "C" int ghm_risk_zsc(const ghm_model_t* text, int64_t B, const float* i_pp, const void* t_leaves, int leaf_dtype,
+                            double* sums, void* stream) {
+    if (!text || !i_pp || !t_leaves || !sums) return ghm_fail(GHM_EINVAL, "ghm_risk_zsc: null argument");
+    if (B <= 0) return GHM_OK;
+    if (leaf_dtype != GHM_LEAF_I64 && leaf_dtype != GHM_LEAF_U8) return ghm_fail(GHM_EINVAL, "bad leaf_dtype %d", leaf_dtype);
+    const GhmDev& d = text->d;
+    const unsigned grid = (unsigned)std::min<int64_t>((B + RISK_NT - 1) / RISK_NT, 148 * 8);
+    cudaStream_t st = (cudaStream_t)stream;
+#define ZSC_GO(Q)                                                                                           \
+    do {                                                                                                    \
+        if (leaf_dtype == GHM_LEAF_I64)                                                                     \
+            k_risk_zsc<Q, int64_t><<<grid, RISK_NT, 0, st>>>(d, i_pp, (const int64_t*)t_leaves, B, sums);   \
+        else                                                                                                \
+            k_risk_zsc<Q, uint8_t><<<grid, RISK_NT, 0, st>>>(d, i_pp, (const uint8_t*)t_leaves, B, sums);   \
+    } while (0)
+    switch (ghm_pad_q(d.q)) {
+        case 4: ZSC_GO(4); break;
+        case 8: ZSC_GO(8); break;
+        case 10: ZSC_GO(10); break;
+        case 16: ZSC_GO(16); break;
+        default: return ghm_fail(GHM_EUNSUP, "ghm_risk_zsc covers q <= %d in this build", GHM_MAX_Q_REG);
+    }
+#undef ZSC_GO
     GHM_CHECK_LAUNCH();
     return GHM_OK;
 }

@@ -42,6 +42,7 @@ SIGNATURES = {
     "ghm_risk_clip": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_vp, c_vp]),
     "ghm_risk_cdm": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp]),
     "ghm_risk_ce": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "ghm_risk_zsc": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp]),
     "ghm_gauss_noise": (c_int, [c_vp, c_i64, c_vp, c_int, c_f, c_u64, c_u64, c_vp, c_vp]),
     "ghm_host_clip_bayes": (c_int, [c_vp, c_vp, c_i64, c_int, c_u64, c_u64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
 }

@@ -33,6 +33,7 @@ from .sharding import all_reduce_sums, dist_info, mean_se_from_sums, shard_range
 __all__ = ["PPCLIPLoss", "GenTransition", "Node", "GHMTree", "SingleSampler", "DoubleSampler",
            "ClassificationSampler", "DenoiseSampler", "ClipSampler", "clip_loss_compute",
            "ConditionalDenoiseSampler", "NextWordPredictSampler", "np", "torch", "nn", "tqdm"]
+# additions (not in the reference module): zeroshot_bayes
 
 
 def _cuda_device(device=None):
@@ -491,6 +492,18 @@ class DoubleSampler(_SamplerBase):
         return (np.array(text_tree.leaves_values).T, np.array(image_tree.leaves_values).T,
                 np.array(text_tree.posterior_probability_CLS).T, np.array(image_tree.posterior_probability_CLS).T,
                 np.array(text_tree.root_value))
+
+
+def zeroshot_bayes(sampler, batch_size=7500):
+    """Zero-shot classification Bayes risk of a DoubleSampler: the recipe of figures/eval-zsc-risk.py:66-83
+    (get_zeroshot_batch, image root posterior pushed through t_transition[l][0], float32 CE against the first text
+    leaf) with the projection and the reduction on the device.  Returns (mean, std / sqrt(n))."""
+    _, text_tree, image_tree = sampler._paired_trees(batch_size)
+    text_tree.BP_CLS()
+    image_tree.BP_CLS()
+    sums = ops.risk_zsc(sampler.t_model, image_tree._post, text_tree._leaves)
+    mean, se = mean_se_from_sums(sums)
+    return np.float64(mean), np.float64(se)
 
 
 def _tree_from_device(sampler, which, out, batch_size):

@@ -340,6 +340,18 @@ def risk_ce(pp, target, sums=None, target_stride=1, target_offset=0, row_group=1
     return sums
 
 
+def risk_zsc(text_model, i_pp, t_leaves, sums=None):
+    """Accumulate the zero-shot CE: image root posterior pushed down the text tree's leftmost path vs the first text leaf."""
+    i_pp, t_leaves = i_pp.contiguous(), t_leaves.contiguous()
+    assert i_pp.dtype == torch.float32 and i_pp.shape[0] == t_leaves.shape[0]
+    with torch.cuda.device(i_pp.device):
+        if sums is None:
+            sums = new_sums(i_pp.device)
+        check(text_model._lib.ghm_risk_zsc(text_model._h, i_pp.shape[0], _ptr(i_pp), _ptr(t_leaves), _leaf_code(t_leaves),
+                                           _ptr(sums), _stream()))
+    return sums
+
+
 def mean_se(sums, se_count=None):
     """(mean, std/sqrt(se_count)) from {sum, sumsq, count}; population std like np.std (reference :41,817,894)."""
     s1, s2, c = (float(x) for x in sums.tolist())

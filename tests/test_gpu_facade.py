@@ -56,6 +56,11 @@ def test_kat_zsc_bayes(G, kat):
                                              torch.tensor(tl, dtype=torch.long)[:, 0]).item()
     assert loss == pytest.approx(kat["zsc-risk.json"]["Bayes"][9], rel=1e-5)
     assert tl.shape == (7500, 81) and tl.dtype == np.int64 and tpp.shape == (7500, 10) and tpp.dtype == np.float64
+    # the same recipe with the projection + CE reduction on the device (ghm_risk_zsc): two more grid points
+    for idx, p in ((9, .2), (0, .02)):
+        s2 = G.DoubleSampler(n_layers=[4, 4], n_childs=[3, 3], variable_type=10, p_ys=[u10, u10], p_flips=[p, p], seedtree=42)
+        val, se = G.zeroshot_bayes(s2, 7500)
+        assert val == pytest.approx(kat["zsc-risk.json"]["Bayes"][idx], rel=2e-5) and 0 < se < 0.1
 
 
 def test_clip_get_batch_structure_and_values(G, gold):
