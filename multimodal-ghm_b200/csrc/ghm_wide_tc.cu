@@ -16,9 +16,16 @@
 //     TMEM; tcgen05.commit arrives on the stage's mbarrier so the stage can be refilled while later MMAs run;
 //   * epilogue: each warp reads its 32 TMEM lanes with tcgen05.ld.32x32b.x32 and writes full 128-byte row
 //     segments of Y.
+// k_wide_gemm_tma (TF32): the same tile computed by a warp-specialised CTA fed by TMA -- warp 0 issues
+// cp.async.bulk.tensor (SWIZZLE_128B tensor maps over the message matrix and the weight table, 128-byte K chunks)
+// into a 2-4 stage ring guarded by full/empty mbarriers, warp 1 issues the MMAs and frees stages with tcgen05.commit,
+// warps 2-5 drain TMEM.  No thread touches the operands: the FP32 bits go HBM/L2 -> shared memory -> tensor core.
+// k_wide_gemm_tc (BF16, and the TF32 fallback) stages operands with ordinary loads because BF16 needs the FP32 ->
+// BF16 conversion in flight.
 // The combine / cavity / belief row kernels around the GEMM are shared with the FP32 path.
 #include "ghm_wide.cuh"
 
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #define TC_THREADS 128
@@ -207,12 +214,181 @@ __global__ void __launch_bounds__(TC_THREADS) k_wide_gemm_tc(const GhmDev d, int
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA-fed, warp-specialised TF32 variant
+// ------------------------------------------------------------------------------------------------
+#define TMA_THREADS 192
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(TMA_THREADS) k_wide_gemm_tma(const __grid_constant__ CUtensorMap mapX,
+                                                               const __grid_constant__ CUtensorMap mapW, const GhmDev d,
+                                                               int64_t B, int level, int stages, float* __restrict__ Y) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = d.QW;
+    const int node = blockIdx.y;
+    const int64_t m0 = (int64_t)blockIdx.x * TC_M;
+    const int mi = d.mat_off[level] + (d.ti ? node - ghm_div_s(node, d) * d.s : node);
+    unsigned char* tiles = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = TC_M * 128, b_bytes = N * 128, stage_bytes = a_bytes + b_bytes;
+    const int nchunks = N / 32;
+    const uint32_t tmem_cols = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                      // ===== TMA producer =====
+            for (int kc = 0; kc < nchunks; ++kc) {
+                const int st = kc % stages;
+                if (kc >= stages) mbar_wait(&empty_bar[st], ((kc / stages) - 1) & 1);
+                unsigned char* At = tiles + (size_t)st * stage_bytes;
+                mbar_expect_tx(&full_bar[st], (uint32_t)stage_bytes);
+                tma_load_2d(At, &mapX, &full_bar[st], kc * 32, (int)((int64_t)node * B + m0));
+                tma_load_2d(At + a_bytes, &mapW, &full_bar[st], kc * 32, mi * N);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                      // ===== MMA issuer =====
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            for (int kc = 0; kc < nchunks; ++kc) {
+                const int st = kc % stages;
+                mbar_wait(&full_bar[st], (kc / stages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                unsigned char* At = tiles + (size_t)st * stage_bytes;
+                const uint64_t adesc = umma_desc_sw128(smem_u32(At)), bdesc = umma_desc_sw128(smem_u32(At + a_bytes));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_issue<GHM_GEMM_TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
+                umma_commit(&empty_bar[st]);                  // stage free once these MMAs have read it
+            }
+            umma_commit(&tmem_full_bar);                      // accumulator complete
+        }
+    } else {                                                  // ===== epilogue warps 2..5 =====
+        const int quarter = warp & 3;                         // TMEM lane quarter this warp may access
+        mbar_wait(&tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t row = m0 + quarter * 32 + lane;
+        float* Yn = Y + (int64_t)node * B * N;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < B) {
+                uint4* dst = reinterpret_cast<uint4*>(Yn + row * N + c0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// 2-D FP32 row-major [rows, N] tensor map with a [box_rows x 32] box (128-byte rows, SWIZZLE_128B)
+static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, int N, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)N * sizeof(float)};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// returns GHM_EUNSUP when TMA cannot be used (no driver entry point, misaligned pointer): caller falls back
+static int launch_gemm_tma(const ghm_model* m, int64_t B, int level, int n_nodes, int down, const float* X, float* Y,
+                           cudaStream_t st) {
+    const GhmDev& d = m->d;
+    const int N = d.QW;
+    if (((uintptr_t)X % 16) != 0 || ((uintptr_t)Y % 16) != 0) return GHM_EUNSUP;
+    if ((int64_t)n_nodes * B >= (1ll << 31)) return GHM_EUNSUP;
+    CUtensorMap mapX, mapW;
+    if (!make_map(&mapX, X, (uint64_t)n_nodes * (uint64_t)B, N, TC_M)) return GHM_EUNSUP;
+    if (!make_map(&mapW, down ? d.Wdn : d.Wup, (uint64_t)d.n_mat * (uint64_t)N, N, N)) return GHM_EUNSUP;
+    const int stage_bytes = TC_M * 128 + N * 128;
+    const int nchunks = N / 32;
+    int stages = std::min(4, nchunks);
+    while (stages > 2 && (size_t)stages * stage_bytes + 1024 > 110 * 1024) --stages;     // two CTAs per SM
+    const size_t dyn = (size_t)stages * stage_bytes + 1024;
+    GHM_CUDA_TRY(cudaFuncSetAttribute(k_wide_gemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    dim3 grid((unsigned)((B + TC_M - 1) / TC_M), (unsigned)n_nodes);
+    k_wide_gemm_tma<<<grid, TMA_THREADS, dyn, st>>>(mapX, mapW, d, B, level, stages, Y);
+    GHM_CHECK_LAUNCH();
+    return GHM_OK;
+}
+
 int ghm_wide_gemm_tc(const ghm_model* m, int64_t B, int level, int n_nodes, int down, const float* X, float* Y, cudaStream_t st) {
     const GhmDev& d = m->d;
     const int N = d.QW;
     if (N != 64 && N != 128 && N != 192 && N != 256) return GHM_EUNSUP;
     if (n_nodes > 65535) return GHM_EUNSUP;
     const int kind = m->gemm_mode;
+    if (kind == GHM_GEMM_TF32) {
+        const int rc = launch_gemm_tma(m, B, level, n_nodes, down, X, Y, st);
+        if (rc != GHM_EUNSUP) return rc;
+    }
     const int kchunk = kind == GHM_GEMM_TF32 ? 32 : 64;
     const int nchunks = N / kchunk;
     const int stage_bytes = TC_M * 128 + N * 128;
