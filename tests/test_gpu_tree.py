@@ -222,3 +222,35 @@ def test_paired_sampling_redraws_partner_roots(ops):
     assert torch.equal(got_r, ref_r) and torch.equal(got_l, ref_l) and torch.equal(got_p, ref_p)
     assert torch.equal(got_r[:n_shared], t["root"][:n_shared])
     assert not torch.equal(got_r[n_shared:], t["root"][n_shared:])
+
+
+def test_full_size_properties_c2(ops):
+    """BASELINE configs[1] at its full size (65 536 pairs -> 327 680 trees per modality), through size-independent
+    properties: leaves in range, posteriors normalised, BP on the produced leaves reproduces the fused posterior
+    (sample -> BP idempotence), uint8 and int64 leaves agree, two shards of the global batch equal the whole, and a
+    checksum of the leaves is invariant to how the batch is split across launches."""
+    from oracle import ghm_oracle as O
+    u = np.ones(10) / 10
+    mo = O.PairedModel([4, 4], [3, 3], [u, u], [.2, .2])
+    tm = ops.GhmModel(mo.t_T, 4, 3, 10, device="cuda:0")
+    B, seed = 5 * 65536, 2024
+    a = tm.sample(B, seed=seed, root_mode=ops.ROOT_UNIFORM, want_post=True, want_root_hd=True)
+    lv, post = a["leaves"], a["post"]
+    assert int(lv.min()) >= 0 and int(lv.max()) <= 9 and int(a["root"].min()) >= 0 and int(a["root"].max()) <= 9
+    assert torch.allclose(post.sum(1), torch.ones(B, device="cuda:0"), atol=2e-6) and bool((post >= 0).all())
+    assert float(a["root_hd"].max(1).values.abs().max()) < 1e-5                      # max-shifted log-likelihood
+    p2, h2 = tm.bp_cls(lv)
+    assert torch.allclose(p2, post, rtol=2e-5, atol=1e-7)
+    u8 = tm.sample(B, seed=seed, root_mode=ops.ROOT_UNIFORM, leaf_dtype=torch.uint8, want_post=True)
+    assert torch.equal(u8["leaves"].long(), lv) and torch.equal(u8["post"], post)
+    cut = 123457                                                                      # odd split, not a tile multiple
+    s1 = tm.sample(cut, seed=seed, tree_offset=0, root_mode=ops.ROOT_UNIFORM, want_post=True)
+    s2 = tm.sample(B - cut, seed=seed, tree_offset=cut, root_mode=ops.ROOT_UNIFORM, want_post=True)
+    assert torch.equal(torch.cat([s1["leaves"], s2["leaves"]]), lv)
+    assert torch.equal(torch.cat([s1["post"], s2["post"]]), post)
+    w = torch.arange(1, 82, device="cuda:0", dtype=torch.int64)
+    assert int((lv * w).sum()) == int((s1["leaves"] * w).sum()) + int((s2["leaves"] * w).sum())
+    # the root posterior should put most mass on the true root at p_flip = 0.2 (sanity of the whole pipeline)
+    acc = float((post.argmax(1) == a["root"]).float().mean())
+    assert 0.5 < acc <= 1.0
+    assert tm.status() == 0
