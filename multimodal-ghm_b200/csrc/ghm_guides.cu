@@ -30,16 +30,34 @@ struct LvlArgs {
     float* post; float* root_hd; float* mean;
 };
 
+// compact message rows are q floats, 8-byte aligned when q is even: move them as float2 (half the memory
+// transactions of scalar accesses at a 4q-byte stride)
 template <int Q>
 __device__ __forceinline__ void load_vec(const float* p, float (&v)[Q], int q) {
+    if ((q & 1) == 0 && (reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+        const float2* p2 = reinterpret_cast<const float2*>(p);
 #pragma unroll
-    for (int k = 0; k < Q; ++k) v[k] = (k < q) ? p[k] : -INFINITY;
+        for (int k = 0; k < Q; k += 2) {
+            if (k < q) { const float2 t = p2[k >> 1]; v[k] = t.x; v[k + 1] = t.y; }
+            else { v[k] = -INFINITY; v[k + 1] = -INFINITY; }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v[k] = (k < q) ? p[k] : -INFINITY;
+    }
 }
 template <int Q>
 __device__ __forceinline__ void store_vec(float* p, const float (&v)[Q], int q) {
+    if ((q & 1) == 0 && (reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+        float2* p2 = reinterpret_cast<float2*>(p);
 #pragma unroll
-    for (int k = 0; k < Q; ++k)
-        if (k < q) p[k] = v[k];
+        for (int k = 0; k < Q; k += 2)
+            if (k < q) p2[k >> 1] = make_float2(v[k], v[k + 1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < Q; ++k)
+            if (k < q) p[k] = v[k];
+    }
 }
 
 // out[a] = log(sum_b T[a][b] exp(h[b] - m)) + m   with m = max h   (== log(T @ exp(h)) without overflow)
@@ -266,6 +284,7 @@ __global__ void __launch_bounds__(256) k_expand_all(const __grid_constant__ Expa
     for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
         float* out = t.out + b * (int64_t)upt * W;
         const int64_t sbase = b * (int64_t)a.n_nodes * q;
+#pragma unroll 4
         for (int u = threadIdx.x; u < upt; u += 256) {
             const int i = div_magic(u, C2, C2_magic);
             const int j = u - i * C2;

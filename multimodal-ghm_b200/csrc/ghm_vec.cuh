@@ -81,17 +81,6 @@ __device__ __forceinline__ void ghm_normalize(float (&x)[Q]) {
     for (int k = 0; k < Q; ++k) x[k] *= inv;
 }
 
-// Philox-mode inverse CDF: child = #{k < q-1 : r >= thr[k]}   (thr = floor(cdf * 2^32))
-template <int Q>
-__device__ __forceinline__ int ghm_search_u32(const uint32_t* __restrict__ row, uint32_t r, int q) {
-    uint32_t thr[Q];
-    ghm_load_row<Q, uint32_t>(row, thr);
-    int cnt = 0;
-#pragma unroll
-    for (int k = 0; k < Q - 1; ++k) cnt += (r >= thr[k]) ? 1 : 0;
-    return min(cnt, q - 1);
-}
-
 // parity-mode inverse CDF: first k with u < cdf[k], else 0   (reference argmax semantics, :164-165)
 __device__ __forceinline__ int ghm_search_f64(const double* __restrict__ row, double u, int q) {
     int lo = 0, hi = q;                                  // cdf is non-decreasing: lower bound of {k : u < cdf[k]}
