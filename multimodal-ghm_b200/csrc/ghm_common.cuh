@@ -26,7 +26,7 @@
 //   cdfd  [m][a][k]   f64  sequential cumsum, unpadded stride q                     (parity mode)
 // ------------------------------------------------------------------------------------
 struct GhmDev {
-    int L, s, q, QP, QS, QW, ti;                // QW = roundup(q, 64): row stride of the wide (q > 16) path, 0 when q <= 16
+    int L, s, q, QP, QS, QW, ti;                // QW = roundup(q, 32): row stride of the wide (q > 16) path, 0 when q <= 16
     int n_mat;
     int n_leaves;                          // s^L
     int n_edges;                           // sum_{l=1..L} s^l

@@ -148,7 +148,7 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     d.L = L; d.s = s; d.q = q; d.ti = ti ? 1 : 0;
     d.QP = ghm_pad_q(q) ? ghm_pad_q(q) : (int)align_up(q, 4);
     d.QS = (int)align_up(d.QP, 4);
-    d.QW = q > GHM_MAX_Q_REG ? (int)align_up(q, 64) : 0;
+    d.QW = q > GHM_MAX_Q_REG ? (int)align_up(q, 32) : 0;
     d.spow[0] = 1;
     for (int l = 1; l <= L; ++l) d.spow[l] = d.spow[l - 1] * s;
     for (int l = L + 1; l <= GHM_MAX_LEVELS; ++l) d.spow[l] = 0;

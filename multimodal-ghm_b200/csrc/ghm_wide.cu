@@ -5,7 +5,7 @@
 // product of the north star is a real dense contraction:
 //
 //   layout    messages of one tree level live NODE-major: M[node][tree][QW] f32 (QW = q rounded up to
-//             64, zero padded), so "every tree's message at node v" is one contiguous [B, QW] matrix and
+//             32, zero padded), so "every tree's message at node v" is one contiguous [B, QW] matrix and
 //             the child->parent step `T_v @ m` (:207,497) for all trees is the GEMM  U_v = M_v * T_v^T;
 //             nodes of a level are the GEMM batch (blockIdx.z), the weight is picked per node
 //             (translation-invariant: (level, child index); per-edge: the edge) -- no gather, no scatter.
@@ -245,29 +245,30 @@ __global__ void __launch_bounds__(WR_NT) k_wide_belief(const GhmDev d, int64_t B
 
 // ------------------------------------------------------------------------------------------------
 // FP32 batched row-GEMM on CUDA cores:  Y[node][b][n] = sum_k X[node][b][k] * W[mat(node)][k][n]
-// CTA tile 128 (trees) x 64 (n), K step 16, 256 threads, thread tile 8 x 4, double-buffered smem.
+// CTA tile 128 (trees) x 64 (or 32) columns, K step 16, 256 threads, thread tile 8 x 4 (8 x 2), double-buffered smem.
 // ------------------------------------------------------------------------------------------------
 #define SG_BM 128
-#define SG_BN 64
 #define SG_BK 16
+template <int BN>                                               // 64, or 32 when QW is an odd multiple of 32
 __global__ void __launch_bounds__(256) k_wide_sgemm(const GhmDev d, int64_t B, int level, int down, const float* __restrict__ X,
                                                     float* __restrict__ Y) {
+    constexpr int TN = BN / 16;                                 // columns per thread: 4 or 2
     __shared__ __align__(16) float As[2][SG_BK][SG_BM + 4];     // [k][m] (transposed on load)
-    __shared__ __align__(16) float Bs[2][SG_BK][SG_BN];         // [k][n]
+    __shared__ __align__(16) float Bs[2][SG_BK][BN];            // [k][n]
     const int QW = d.QW, tid = threadIdx.x;
     const int node = blockIdx.z;
     const int64_t m0 = (int64_t)blockIdx.x * SG_BM;
-    const int n0 = blockIdx.y * SG_BN;
+    const int n0 = blockIdx.y * BN;
     const float* W = (down ? d.Wup : d.Wdn) + (size_t)wide_mat(d, level, node) * QW * QW;   // W[k][n]
     const float* Xn = X + (int64_t)node * B * QW;
     float* Yn = Y + (int64_t)node * B * QW;
-    const int tm = (tid >> 4) * 8, tn = (tid & 15) * 4;
-    float acc[8][4];
+    const int tm = (tid >> 4) * 8, tn = (tid & 15) * TN;
+    float acc[8][TN];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    // load mapping: A tile 128 x 16 floats = 512 float4 (2 per thread); B tile 16 x 64 = 256 float4 (1 per thread)
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    // load mapping: A tile 128 x 16 floats = 512 float4 (2 per thread); B tile 16 x BN = 4*BN float4
     auto load_tiles = [&](int buf, int k0) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(256) k_wide_sgemm(const GhmDev d, int64_t B, i
             if (m0 + m < B) v = *reinterpret_cast<const float4*>(Xn + (m0 + m) * QW + k0 + kq);
             As[buf][kq + 0][m] = v.x; As[buf][kq + 1][m] = v.y; As[buf][kq + 2][m] = v.z; As[buf][kq + 3][m] = v.w;
         }
-        {
-            const int k = tid >> 4, nq = (tid & 15) * 4;
+        if (tid < 4 * BN) {
+            const int k = tid / (BN / 4), nq = (tid % (BN / 4)) * 4;
             *reinterpret_cast<float4*>(&Bs[buf][k][nq]) = *reinterpret_cast<const float4*>(W + (size_t)(k0 + k) * QW + n0 + nq);
         }
     };
@@ -292,22 +293,25 @@ __global__ void __launch_bounds__(256) k_wide_sgemm(const GhmDev d, int64_t B, i
         for (int k = 0; k < SG_BK; ++k) {
             const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tm]);
             const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][tm + 4]);
-            const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][k][tn]);
             const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[TN];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                acc[i][0] = fmaf(a[i], bv.x, acc[i][0]);
-                acc[i][1] = fmaf(a[i], bv.y, acc[i][1]);
-                acc[i][2] = fmaf(a[i], bv.z, acc[i][2]);
-                acc[i][3] = fmaf(a[i], bv.w, acc[i][3]);
-            }
+            for (int j = 0; j < TN; ++j) bv[j] = Bs[buf][k][tn + j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int64_t m = m0 + tm + i;
-        if (m < B) *reinterpret_cast<float4*>(Yn + m * QW + n0 + tn) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (m < B) {
+            float* dst = Yn + m * QW + n0 + tn;
+            if constexpr (TN == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            else *reinterpret_cast<float2*>(dst) = make_float2(acc[i][0], acc[i][1]);
+        }
     }
 }
 
@@ -321,14 +325,15 @@ int ghm_wide_gemm(const ghm_model* m, int64_t B, int level, int n_nodes, int dow
         int rc = ghm_wide_gemm_tc(m, B, level, n_nodes, down, X, Y, st);
         if (rc != GHM_EUNSUP) return rc;                       // shapes the tensor variant does not cover run on CUDA cores
     }
-    for (int n0 = 0; n0 < n_nodes; n0 += 65535) {
-        const int nn = std::min(65535, n_nodes - n0);
-        dim3 grid((unsigned)((B + SG_BM - 1) / SG_BM), (unsigned)(d.QW / SG_BN > 0 ? d.QW / SG_BN : 1), (unsigned)nn);
-        if (d.QW % SG_BN != 0) return ghm_fail(GHM_EUNSUP, "internal: QW=%d is not a multiple of %d", d.QW, SG_BN);
-        if (n0 != 0) return ghm_fail(GHM_EUNSUP, "level with more than 65535 nodes");
-        k_wide_sgemm<<<grid, 256, 0, st>>>(d, B, level, down, X, Y);
-        GHM_CHECK_LAUNCH();
+    if (n_nodes > 65535) return ghm_fail(GHM_EUNSUP, "level with more than 65535 nodes");
+    if (d.QW % 64 == 0) {
+        dim3 grid((unsigned)((B + SG_BM - 1) / SG_BM), (unsigned)(d.QW / 64), (unsigned)n_nodes);
+        k_wide_sgemm<64><<<grid, 256, 0, st>>>(d, B, level, down, X, Y);
+    } else {
+        dim3 grid((unsigned)((B + SG_BM - 1) / SG_BM), (unsigned)(d.QW / 32), (unsigned)n_nodes);
+        k_wide_sgemm<32><<<grid, 256, 0, st>>>(d, B, level, down, X, Y);
     }
+    GHM_CHECK_LAUNCH();
     return GHM_OK;
 }
 
