@@ -60,26 +60,28 @@ __device__ __forceinline__ void store_vec(float* p, const float (&v)[Q], int q) 
     }
 }
 
-// out[a] = log(sum_b T[a][b] exp(h[b] - m)) + m   with m = max h   (== log(T @ exp(h)) without overflow)
+// out[a] = log(sum_b T[a][b] exp(h[b] - m)) + m   with m = max h   (== log(T @ exp(h)) without overflow).
+// MUFU-based __expf / __logf: arguments are <= 0 / sums in (0, q], where their error (<= 2 ulp resp. 2^-21.4 absolute)
+// is far inside the 1e-5 budget; the precise library versions made these kernels instruction bound.
 template <int Q>
 __device__ __forceinline__ void log_matvec(const float* __restrict__ T, const float (&h)[Q], float (&out)[Q], int q) {
     const float m = ghm_vmax<Q>(h);
     float e[Q], u[Q];
 #pragma unroll
-    for (int k = 0; k < Q; ++k) e[k] = (k < q) ? expf(h[k] - m) : 0.f;
+    for (int k = 0; k < Q; ++k) e[k] = (k < q) ? __expf(h[k] - m) : 0.f;
     ghm_matvec<Q>(T, e, u);
 #pragma unroll
-    for (int k = 0; k < Q; ++k) out[k] = (k < q) ? logf(u[k]) + m : -INFINITY;
+    for (int k = 0; k < Q; ++k) out[k] = (k < q) ? __logf(u[k]) + m : -INFINITY;
 }
 template <int Q>
 __device__ __forceinline__ void log_matvec_t(const float* __restrict__ T, const float (&h)[Q], float (&out)[Q], int q) {
     const float m = ghm_vmax<Q>(h);
     float e[Q], u[Q];
 #pragma unroll
-    for (int k = 0; k < Q; ++k) e[k] = (k < q) ? expf(h[k] - m) : 0.f;
+    for (int k = 0; k < Q; ++k) e[k] = (k < q) ? __expf(h[k] - m) : 0.f;
     ghm_matvec_t<Q>(T, e, u);
 #pragma unroll
-    for (int k = 0; k < Q; ++k) out[k] = (k < q) ? logf(u[k]) + m : -INFINITY;
+    for (int k = 0; k < Q; ++k) out[k] = (k < q) ? __logf(u[k]) + m : -INFINITY;
 }
 
 __device__ __forceinline__ int leaf_at(const void* leaves, int dtype, int64_t off, int q, int* status) {
@@ -109,13 +111,10 @@ __device__ __forceinline__ LvlThread lvl_thread(const GhmDev& d, int64_t B, int 
 static unsigned lvl_grid(const GhmDev& d, int64_t B, int l) { return (unsigned)((B * d.spow[l] + GD_NT - 1) / GD_NT); }
 
 // ---- BP_CLS, log domain (reference :185-221): nodes of depth l, bottom-up --------------------------
+// node (depth l, idx) of tree b; HD = this tree's compact rows [n_int][q] (global or shared memory)
 template <int Q>
-__global__ void __launch_bounds__(GD_NT) k_lvl_cls(const GhmDev d, const LvlArgs a, int l) {
-    const LvlThread th = lvl_thread(d, a.B, l);
-    if (!th.ok) return;
-    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves, idx = th.idx;
-    const int64_t b = th.b;
-    float* HD = a.HD + b * (int64_t)a.n_nodes * q;
+__device__ __forceinline__ void cls_node(const GhmDev& d, const LvlArgs& a, int64_t b, int l, int idx, float* HD) {
+    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves;
     float acc[Q];
 #pragma unroll
     for (int k = 0; k < Q; ++k) acc[k] = (k < q) ? 0.f : -INFINITY;
@@ -159,16 +158,18 @@ __global__ void __launch_bounds__(GD_NT) k_lvl_cls(const GhmDev d, const LvlArgs
     }
 }
 
-// ---- BP_DNS, log domain (reference :467-523): upward pass, nodes of depth l ------------------------
 template <int Q>
-__global__ void __launch_bounds__(GD_NT) k_lvl_dns_up(const GhmDev d, const LvlArgs a, int l) {
+__global__ void __launch_bounds__(GD_NT) k_lvl_cls(const GhmDev d, const LvlArgs a, int l) {
     const LvlThread th = lvl_thread(d, a.B, l);
     if (!th.ok) return;
-    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves, idx = th.idx;
-    const int64_t b = th.b;
-    const int64_t base = b * (int64_t)a.n_nodes * q;
-    float* HD = a.HD + base;
-    float* QD = a.QD + base;
+    cls_node<Q>(d, a, th.b, l, th.idx, a.HD + th.b * (int64_t)a.n_nodes * d.q);
+}
+
+// ---- BP_DNS, log domain (reference :467-523): upward pass, nodes of depth l ------------------------
+template <int Q>
+__device__ __forceinline__ void dns_up_node(const GhmDev& d, const LvlArgs& a, int64_t b, int l, int idx, float* HD, float* QD,
+                                            float* BU) {
+    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves;
     const int node = node_off_all(d, l) + idx;
     float acc[Q];
     if (l == L) {                                             // leaves: hd unshifted (:485), qd = log(T @ exp(hd)) (:487)
@@ -205,24 +206,29 @@ __global__ void __launch_bounds__(GD_NT) k_lvl_dns_up(const GhmDev d, const LvlA
             if (k < q) acc[k] += a.ext[b * q + k];
     }
     store_vec<Q>(HD, acc, q);
-    store_vec<Q>(a.BU + base, acc, q);
+    store_vec<Q>(BU, acc, q);
+}
+
+template <int Q>
+__global__ void __launch_bounds__(GD_NT) k_lvl_dns_up(const GhmDev d, const LvlArgs a, int l) {
+    const LvlThread th = lvl_thread(d, a.B, l);
+    if (!th.ok) return;
+    const int64_t base = th.b * (int64_t)a.n_nodes * d.q;
+    dns_up_node<Q>(d, a, th.b, l, th.idx, a.HD + base, a.QD + base, a.BU + base);
 }
 
 // ---- BP_DNS downward pass: bu = hd + log(T^T @ exp(bu_parent - qd)) - max (:509-514), nodes of depth l >= 1 ----
 template <int Q>
-__global__ void __launch_bounds__(GD_NT) k_lvl_dns_down(const GhmDev d, const LvlArgs a, int l) {
-    const LvlThread th = lvl_thread(d, a.B, l);
-    if (!th.ok) return;
-    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves, idx = th.idx;
-    const int64_t b = th.b;
-    const int64_t base = b * (int64_t)a.n_nodes * q;
+__device__ __forceinline__ void dns_down_node(const GhmDev& d, const LvlArgs& a, int64_t b, int l, int idx, float* HD, float* QD,
+                                              float* BU) {
+    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves;
     const int node = node_off_all(d, l) + idx;
     const int pidx = ghm_div_s(idx, d);
     const int par = node_off_all(d, l - 1) + pidx;
     float bp[Q], qv[Q], hv[Q], m[Q];
-    load_vec<Q>(a.BU + base + (int64_t)par * q, bp, q);
-    load_vec<Q>(a.QD + base + (int64_t)node * q, qv, q);
-    load_vec<Q>(a.HD + base + (int64_t)node * q, hv, q);
+    load_vec<Q>(BU + (int64_t)par * q, bp, q);
+    load_vec<Q>(QD + (int64_t)node * q, qv, q);
+    load_vec<Q>(HD + (int64_t)node * q, hv, q);
 #pragma unroll
     for (int k = 0; k < Q; ++k) bp[k] = (k < q) ? bp[k] - qv[k] : -INFINITY;
     const int mi = d.mat_off[l] + (d.ti ? idx - pidx * s : idx);
@@ -232,13 +238,21 @@ __global__ void __launch_bounds__(GD_NT) k_lvl_dns_down(const GhmDev d, const Lv
     const float mx = ghm_vmax<Q>(m);
 #pragma unroll
     for (int k = 0; k < Q; ++k) m[k] -= mx;
-    store_vec<Q>(a.BU + base + (int64_t)node * q, m, q);
+    store_vec<Q>(BU + (int64_t)node * q, m, q);
     if (l == L && a.mean) {                                                   // (:516-519)
         float num = 0.f, den = 0.f;
 #pragma unroll
         for (int k = 0; k < Q; ++k) { const float e = (k < q) ? expf(m[k]) : 0.f; num += (float)k * e; den += e; }
         a.mean[b * nL + idx] = num / den;
     }
+}
+
+template <int Q>
+__global__ void __launch_bounds__(GD_NT) k_lvl_dns_down(const GhmDev d, const LvlArgs a, int l) {
+    const LvlThread th = lvl_thread(d, a.B, l);
+    if (!th.ok) return;
+    const int64_t base = th.b * (int64_t)a.n_nodes * d.q;
+    dns_down_node<Q>(d, a, th.b, l, th.idx, a.HD + base, a.QD + base, a.BU + base);
 }
 
 // ---- expansion: node messages -> [B, n_L, C] guide tensors ------------------------------------------
@@ -326,6 +340,113 @@ static int expand_launch(const ExpandAll& a, cudaStream_t st) {
     return GHM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tree-tiled fused guide kernels: a CTA owns G consecutive trees, runs the whole log-domain BP level by level on
+// compact message rows held in SHARED memory (no HBM round trip of the node messages, no per-level launches), then
+// streams every guide tensor of its trees -- one contiguous span of G rows per tensor -- as 8-byte units straight
+// from shared memory.  HBM traffic = the inputs + the guide tensors, i.e. the algorithmic bytes.
+// ------------------------------------------------------------------------------------------------
+#define GF_NT 128
+template <bool VEC2>
+__device__ __forceinline__ void expand_from_smem(const ExpandAll& e, const float* s0, const float* s1, const float* s2,
+                                                 int tree_stride, int64_t tree0, int g) {
+    const int q = e.q, W = VEC2 ? 2 : 1;
+    const int hq = q / W;
+    const unsigned hq_magic = hq >= 2 ? (unsigned)((0x100000000ull + (unsigned)hq - 1) / (unsigned)hq) : 0u;
+    for (int ti = 0; ti < e.n_t; ++ti) {
+        const ExpandT& t = e.t[ti];
+        const int C2 = t.nsrc * hq;
+        const int upt = e.nL * C2;
+        const unsigned C2_magic = C2 >= 2 ? (unsigned)((0x100000000ull + (unsigned)C2 - 1) / (unsigned)C2) : 0u;
+        const unsigned upt_magic = upt >= 2 ? (unsigned)((0x100000000ull + (unsigned)upt - 1) / (unsigned)upt) : 0u;
+        const int R = e.R[t.level]; const unsigned Rm = e.R_magic[t.level];
+        const int noff = e.node_off[t.level];
+        const float* p0 = t.src[0] == 0 ? s0 : (t.src[0] == 1 ? s1 : s2);
+        const float* p1 = t.nsrc > 1 ? (t.src[1] == 0 ? s0 : (t.src[1] == 1 ? s1 : s2)) : p0;
+        const float* p2 = t.nsrc > 2 ? (t.src[2] == 0 ? s0 : (t.src[2] == 1 ? s1 : s2)) : p0;
+        float* out = t.out + tree0 * (int64_t)upt * W;
+        const int total = g * upt;
+#pragma unroll 4
+        for (int u = threadIdx.x; u < total; u += GF_NT) {
+            const int tr = div_magic(u, upt, upt_magic);
+            const int ul = u - tr * upt;
+            const int i = div_magic(ul, C2, C2_magic);
+            const int j = ul - i * C2;
+            const int part = (j >= hq) + (j >= 2 * hq);
+            const int kk = j - part * hq;
+            const int node = noff + div_magic(i, R, Rm);
+            const float* src = (part == 0 ? p0 : (part == 1 ? p1 : p2)) + tr * tree_stride + node * q + kk * W;
+            if (VEC2) reinterpret_cast<float2*>(out)[u] = *reinterpret_cast<const float2*>(src);
+            else out[u] = *src;
+        }
+    }
+}
+
+template <int Q, bool VEC2>
+__global__ void __launch_bounds__(GF_NT) k_guides_dns_fused(const GhmDev d, const LvlArgs a, const __grid_constant__ ExpandAll e,
+                                                            int G) {
+    extern __shared__ __align__(16) float gsm[];
+    const int q = d.q, L = d.L;
+    const int stride = a.n_nodes * q;                       // floats per tree per array
+    float* HD = gsm; float* QD = HD + (size_t)G * stride; float* BU = QD + (size_t)G * stride;
+    const int64_t tree0 = (int64_t)blockIdx.x * G;
+    const int g = (int)min((int64_t)G, a.B - tree0);
+    for (int l = L; l >= 0; --l) {
+        const int n = d.spow[l];
+        const unsigned nm = n >= 2 ? (unsigned)((0x100000000ull + (unsigned)n - 1) / (unsigned)n) : 0u;
+        for (int w = threadIdx.x; w < g * n; w += GF_NT) {
+            const int t = div_magic(w, n, nm), idx = w - t * n;
+            dns_up_node<Q>(d, a, tree0 + t, l, idx, HD + t * stride, QD + t * stride, BU + t * stride);
+        }
+        __syncthreads();
+    }
+    for (int l = 1; l <= L; ++l) {
+        const int n = d.spow[l];
+        const unsigned nm = n >= 2 ? (unsigned)((0x100000000ull + (unsigned)n - 1) / (unsigned)n) : 0u;
+        for (int w = threadIdx.x; w < g * n; w += GF_NT) {
+            const int t = div_magic(w, n, nm), idx = w - t * n;
+            dns_down_node<Q>(d, a, tree0 + t, l, idx, HD + t * stride, QD + t * stride, BU + t * stride);
+        }
+        __syncthreads();
+    }
+    expand_from_smem<VEC2>(e, HD, QD, BU, stride, tree0, g);
+}
+
+template <int Q, bool VEC2>
+__global__ void __launch_bounds__(GF_NT) k_guides_cls_fused(const GhmDev d, const LvlArgs a, const __grid_constant__ ExpandAll e,
+                                                            int G) {
+    extern __shared__ __align__(16) float gsm[];
+    const int q = d.q, L = d.L;
+    const int stride = a.n_nodes * q;
+    float* HD = gsm;
+    const int64_t tree0 = (int64_t)blockIdx.x * G;
+    const int g = (int)min((int64_t)G, a.B - tree0);
+    for (int l = L - 1; l >= 0; --l) {
+        const int n = d.spow[l];
+        const unsigned nm = n >= 2 ? (unsigned)((0x100000000ull + (unsigned)n - 1) / (unsigned)n) : 0u;
+        for (int w = threadIdx.x; w < g * n; w += GF_NT) {
+            const int t = div_magic(w, n, nm), idx = w - t * n;
+            cls_node<Q>(d, a, tree0 + t, l, idx, HD + t * stride);
+        }
+        __syncthreads();
+    }
+    expand_from_smem<VEC2>(e, HD, HD, HD, stride, tree0, g);
+}
+
+// trees per CTA of the fused kernels for `arrays` compact arrays; 0 -> does not fit, use the level kernels
+static int fused_trees_per_cta(int n_nodes, int q, int arrays) {
+    const size_t per_tree = (size_t)arrays * n_nodes * q * sizeof(float);
+    const size_t budget = 70 * 1024;                        // 3 CTAs per SM
+    int G = (int)(budget / per_tree);
+    return G > 16 ? 16 : G;
+}
+
+static bool expand_vec2(const ExpandAll& a) {
+    bool vec2 = (a.q % 2) == 0;
+    for (int i = 0; i < a.n_t; ++i) vec2 = vec2 && ((uintptr_t)a.t[i].out % 8) == 0;
+    return vec2;
+}
+
 template <typename F>
 static int dispatch_q(int q, F&& f) {
     switch (ghm_pad_q(q)) {
@@ -368,13 +489,35 @@ extern "C" int ghm_guides_cls(const ghm_model_t* m, int64_t B, const void* leave
     // Simpler and always safe: use guides[0] (depth L-1 tensor, written FIRST by expansion) is not
     // possible either; so allocate nothing and stage in the root guide, expanding levels L-1..1 first
     // and the root level through a tiny copy of the root messages kept in root_hd/post scratch.
+    if (!root_hd) return ghm_fail(GHM_EINVAL, "ghm_guides_cls: root_hd output is required");
+    LvlArgs a{};
+    a.B = B; a.leaves = leaves; a.leaf_dtype = leaf_dtype; a.n_nodes = (int)n_int;
+    a.post = post; a.root_hd = root_hd;
+    const int G = fused_trees_per_cta((int)n_int, d.q, 1);
+    if (G >= 1) {                                              // tree-tiled fused kernel: messages never leave shared memory
+        ExpandAll e;
+        expand_setup(e, d, B, (int)n_int, nullptr, nullptr, nullptr);
+        for (int j = 0; j < L; ++j) expand_add(e, guides[j], L - 1 - j, 1, 0, 0, 0);
+        const size_t dyn = (size_t)G * n_int * d.q * sizeof(float);
+        const unsigned grid = (unsigned)((B + G - 1) / G);
+        const bool v2 = expand_vec2(e);
+        return dispatch_q(d.q, [&](auto Qc) -> int {
+            constexpr int Q = decltype(Qc)::value;
+            if (v2) {
+                GHM_CUDA_TRY(cudaFuncSetAttribute(k_guides_cls_fused<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                k_guides_cls_fused<Q, true><<<grid, GF_NT, dyn, st>>>(d, a, e, G);
+            } else {
+                GHM_CUDA_TRY(cudaFuncSetAttribute(k_guides_cls_fused<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                k_guides_cls_fused<Q, false><<<grid, GF_NT, dyn, st>>>(d, a, e, G);
+            }
+            GHM_CHECK_LAUNCH();
+            return GHM_OK;
+        });
+    }
+    // large trees: level kernels on a compact store staged inside the root guide tensor, expanded last
     float* HD = guides[L - 1];
     if (n_int > (int64_t)d.n_leaves) return ghm_fail(GHM_EUNSUP, "unexpected tree shape");
-    LvlArgs a{};
-    a.B = B; a.leaves = leaves; a.leaf_dtype = leaf_dtype; a.HD = HD; a.n_nodes = (int)n_int;
-    a.post = post; a.root_hd = root_hd;
-    // the root guide needs hd(root) after HD's storage is overwritten: keep it in root_hd (caller buffer)
-    if (!root_hd) return ghm_fail(GHM_EINVAL, "ghm_guides_cls: root_hd output is required");
+    a.HD = HD;
     int rc = dispatch_q(d.q, [&](auto Qc) -> int {
         constexpr int Q = decltype(Qc)::value;
         for (int l = d.L - 1; l >= 0; --l) {
@@ -423,6 +566,29 @@ extern "C" int ghm_guides_dns(const ghm_model_t* m, int64_t B, const float* z, f
     float* BU = QD + B * nn * d.q;
     LvlArgs a{};
     a.B = B; a.z = z; a.sigma = sigma; a.ext = ext; a.HD = HD; a.QD = QD; a.BU = BU; a.n_nodes = (int)nn; a.mean = mean;
+    const int G = guides ? fused_trees_per_cta((int)nn, d.q, 3) : 0;
+    if (G >= 1) {                                              // tree-tiled fused kernel: messages never leave shared memory
+        ExpandAll e;
+        expand_setup(e, d, B, (int)nn, nullptr, nullptr, nullptr);
+        for (int j = 0; j < L; ++j) expand_add(e, guides[j], L - j, 2, 0, 1, 0);
+        expand_add(e, guides[L], 0, 2, 0, 2, 0);
+        for (int j = 1; j <= L; ++j) expand_add(e, guides[L + j], j, 3, 0, 1, 2);
+        const size_t dyn = (size_t)3 * G * nn * d.q * sizeof(float);
+        const unsigned grid = (unsigned)((B + G - 1) / G);
+        const bool v2 = expand_vec2(e);
+        return dispatch_q(d.q, [&](auto Qc) -> int {
+            constexpr int Q = decltype(Qc)::value;
+            if (v2) {
+                GHM_CUDA_TRY(cudaFuncSetAttribute(k_guides_dns_fused<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                k_guides_dns_fused<Q, true><<<grid, GF_NT, dyn, st>>>(d, a, e, G);
+            } else {
+                GHM_CUDA_TRY(cudaFuncSetAttribute(k_guides_dns_fused<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                k_guides_dns_fused<Q, false><<<grid, GF_NT, dyn, st>>>(d, a, e, G);
+            }
+            GHM_CHECK_LAUNCH();
+            return GHM_OK;
+        });
+    }
     int rc = dispatch_q(d.q, [&](auto Qc) -> int {
         constexpr int Q = decltype(Qc)::value;
         for (int l = d.L; l >= 0; --l) {
