@@ -352,32 +352,54 @@ __device__ __forceinline__ void expand_from_smem(const ExpandAll& e, const float
                                                  int tree_stride, int64_t tree0, int g) {
     const int q = e.q, W = VEC2 ? 2 : 1;
     const int hq = q / W;
-    const unsigned hq_magic = hq >= 2 ? (unsigned)((0x100000000ull + (unsigned)hq - 1) / (unsigned)hq) : 0u;
+    const int ncell = g * e.nL;                               // leaf cells of this CTA's trees, contiguous per tensor
+    const unsigned nL_magic = e.nL >= 2 ? (unsigned)((0x100000000ull + (unsigned)e.nL - 1) / (unsigned)e.nL) : 0u;
     for (int ti = 0; ti < e.n_t; ++ti) {
         const ExpandT& t = e.t[ti];
-        const int C2 = t.nsrc * hq;
-        const int upt = e.nL * C2;
-        const unsigned C2_magic = C2 >= 2 ? (unsigned)((0x100000000ull + (unsigned)C2 - 1) / (unsigned)C2) : 0u;
-        const unsigned upt_magic = upt >= 2 ? (unsigned)((0x100000000ull + (unsigned)upt - 1) / (unsigned)upt) : 0u;
+        const int C2 = t.nsrc * hq;                           // 8-byte units per cell
+        // threads = [cells per iteration][unit within the cell]: the unit's (part, k) is fixed per thread for the whole
+        // tensor and only the cell advances, so the per-store index work is two multiply-high divisions
+        if (C2 < 8) {                                         // narrow cells (cls guides): flat unit index, three divisions
+            const int upt = e.nL * C2, total = g * upt;
+            const unsigned C2_magic = C2 >= 2 ? (unsigned)((0x100000000ull + (unsigned)C2 - 1) / (unsigned)C2) : 0u;
+            const unsigned upt_magic = upt >= 2 ? (unsigned)((0x100000000ull + (unsigned)upt - 1) / (unsigned)upt) : 0u;
+            const float* p0 = t.src[0] == 0 ? s0 : (t.src[0] == 1 ? s1 : s2);
+            const int R0 = e.R[t.level]; const unsigned Rm0 = e.R_magic[t.level];
+            const int noff0 = e.node_off[t.level];
+            float* o = t.out + tree0 * (int64_t)upt * W;
+#pragma unroll 4
+            for (int u = threadIdx.x; u < total; u += GF_NT) {
+                const int tr = div_magic(u, upt, upt_magic);
+                const int ul = u - tr * upt;
+                const int i = div_magic(ul, C2, C2_magic);
+                const int jj = ul - i * C2;
+                const int part = (jj >= hq) + (jj >= 2 * hq);
+                const int kk = jj - part * hq;
+                const float* pb = part == 0 ? p0 : (t.src[part] == 0 ? s0 : (t.src[part] == 1 ? s1 : s2));
+                const float* src = pb + tr * tree_stride + (noff0 + div_magic(i, R0, Rm0)) * q + kk * W;
+                if (VEC2) reinterpret_cast<float2*>(o)[u] = *reinterpret_cast<const float2*>(src);
+                else o[u] = *src;
+            }
+            continue;
+        }
+        const int cpi = GF_NT / C2;                           // >= 1 (C2 <= 3*q/2 <= 24)
+        const int cell0 = (int)threadIdx.x / C2, j = (int)threadIdx.x - cell0 * C2;
+        if (cell0 >= cpi) continue;                           // the few lanes past the last whole cell idle
+        const int part = (j >= hq) + (j >= 2 * hq);
+        const int kk = j - part * hq;
+        const float* pp = t.src[part] == 0 ? s0 : (t.src[part] == 1 ? s1 : s2);
+        pp += kk * W;
         const int R = e.R[t.level]; const unsigned Rm = e.R_magic[t.level];
         const int noff = e.node_off[t.level];
-        const float* p0 = t.src[0] == 0 ? s0 : (t.src[0] == 1 ? s1 : s2);
-        const float* p1 = t.nsrc > 1 ? (t.src[1] == 0 ? s0 : (t.src[1] == 1 ? s1 : s2)) : p0;
-        const float* p2 = t.nsrc > 2 ? (t.src[2] == 0 ? s0 : (t.src[2] == 1 ? s1 : s2)) : p0;
-        float* out = t.out + tree0 * (int64_t)upt * W;
-        const int total = g * upt;
+        float* out = t.out + (tree0 * e.nL) * (int64_t)C2 * W + j * W;
 #pragma unroll 4
-        for (int u = threadIdx.x; u < total; u += GF_NT) {
-            const int tr = div_magic(u, upt, upt_magic);
-            const int ul = u - tr * upt;
-            const int i = div_magic(ul, C2, C2_magic);
-            const int j = ul - i * C2;
-            const int part = (j >= hq) + (j >= 2 * hq);
-            const int kk = j - part * hq;
+        for (int cell = cell0; cell < ncell; cell += cpi) {
+            const int tr = div_magic(cell, e.nL, nL_magic);
+            const int i = cell - tr * e.nL;
             const int node = noff + div_magic(i, R, Rm);
-            const float* src = (part == 0 ? p0 : (part == 1 ? p1 : p2)) + tr * tree_stride + node * q + kk * W;
-            if (VEC2) reinterpret_cast<float2*>(out)[u] = *reinterpret_cast<const float2*>(src);
-            else out[u] = *src;
+            const float* src = pp + tr * tree_stride + node * q;
+            if (VEC2) *reinterpret_cast<float2*>(out + (size_t)cell * C2 * W) = *reinterpret_cast<const float2*>(src);
+            else out[(size_t)cell * C2] = *src;
         }
     }
 }
