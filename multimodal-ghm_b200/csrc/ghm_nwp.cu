@@ -35,11 +35,26 @@ struct NwpArgs {
     float* guides[NWP_MAX_GUIDES];     // only when GUIDE
 };
 
+// rows are q floats, 8-byte aligned for even q: float2 stores (half the transactions of scalar stores at a 4q-byte stride)
+template <int Q>
+__device__ __forceinline__ void store_row(float* dst, const float (&v)[Q], int q) {
+    if ((q & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+        float2* d2 = reinterpret_cast<float2*>(dst);
+#pragma unroll
+        for (int k = 0; k < Q; k += 2)
+            if (k < q) d2[k >> 1] = make_float2(v[k], v[k + 1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < Q; ++k)
+            if (k < q) dst[k] = v[k];
+    }
+}
 template <int Q>
 __device__ __forceinline__ void store_log(float* dst, const float (&v)[Q], int q) {
+    float lg[Q];
 #pragma unroll
-    for (int k = 0; k < Q; ++k)
-        if (k < q) dst[k] = logf(v[k]);
+    for (int k = 0; k < Q; ++k) lg[k] = (k < q) ? __logf(v[k]) : 0.f;      // v in (0, 1]: MUFU.LG2 error << 1e-5 budget
+    store_row<Q>(dst, lg, q);
 }
 
 __device__ __forceinline__ int nwp_leaf(const NwpArgs& a, const GhmDev& d, int64_t off) {
@@ -220,10 +235,9 @@ __global__ void __launch_bounds__(NWP_NT) k_nwp_pos(const GhmDev d, const NwpArg
 #pragma unroll
     for (int k = 0; k < Q; ++k) sum += bel[k];
     const float inv = 1.0f / sum;
-    float* o = a.pp + row * q;
 #pragma unroll
-    for (int k = 0; k < Q; ++k)
-        if (k < q) o[k] = bel[k] * inv;
+    for (int k = 0; k < Q; ++k) bel[k] *= inv;
+    store_row<Q>(a.pp + row * q, bel, q);
 }
 
 // ----------------------------------------------------------------------------------------
