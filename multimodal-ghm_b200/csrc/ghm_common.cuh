@@ -49,8 +49,23 @@ struct GhmDev {
     int* status;                           // sticky device status word
 };
 
+// Source-offset tables of the fused guide kernels (ghm_guides.cu): for every 4- or 8-byte unit of a tree's row in
+// every guide tensor, the shared-memory offset (in floats) of the message element it copies.  A pure function of
+// (L, s, q), so built once at model creation.
+#define GHM_EXP_MAX_T (2 * GHM_MAX_LEVELS + 1)
+struct GhmGuideTab {
+    int G;                                 // trees per CTA the offsets were built for; 0 = fused kernel not usable
+    int n_t;                               // tensors in the guide set
+    int W;                                 // floats per unit (2 when q is even)
+    int stride;                            // floats per tree per message array in shared memory
+    int tab_off[GHM_EXP_MAX_T];            // first table entry of tensor t
+    int upt[GHM_EXP_MAX_T];                // units per tree row of tensor t
+};
+
 struct ghm_model {
     GhmDev d;
+    GhmGuideTab gt_cls, gt_dns;
+    uint16_t* guide_tab;                   // device: cls tables followed by dns tables
     int device;
     int gemm_mode;       // GHM_GEMM_*: arithmetic of the wide path's row-GEMMs
     void* h_slab;        // pinned host image of the slab (table derivation target, source of H2D uploads)
@@ -65,6 +80,8 @@ struct ghm_model {
     void* h_scratch; size_t h_scratch_bytes;
     void* d_scratch; size_t d_scratch_bytes;
 };
+
+int ghm_guides_init(ghm_model* m);        // ghm_guides.cu: builds guide_tab (current device = m->device)
 
 // ------------------------------------------------------------------------------------
 // error plumbing

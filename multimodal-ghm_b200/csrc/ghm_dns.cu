@@ -261,28 +261,11 @@ __global__ void __launch_bounds__(DNS_NT) k_dns(const GhmDev d, const DnsArgs a)
 // ------------------------------------------------------------------------------------------------
 #include "ghm_vec2.cuh"
 
-template <int NW>
-struct __align__(16) DnsTab { float v[NW]; };          // [0, n_mat*Q*Q): TlinT (up) | [n_mat*Q*Q, 2*n_mat*Q*Q): Tlin (down)
-
 struct Dns2Args {
     DnsArgs a;
     int base0, base1, base_leaf;                       // matrix index of child 0 of: edges into depth L-1, L-2, L
     int dn_off;                                        // float offset of the Tlin block inside the table parameter
 };
-
-// y[i] = sum_r T[r][2i..2i+1] * x[r]  with T rows of Q floats (8-byte aligned), table in the constant bank
-template <int Q>
-__device__ __forceinline__ void f2_matvec_c(const float* __restrict__ T, const f2 (&x)[Q / 2], f2 (&y)[Q / 2]) {
-#pragma unroll
-    for (int r = 0; r < Q; ++r) {
-        const float xr = f2_elem<Q>(x, r);
-#pragma unroll
-        for (int i = 0; i < Q / 2; ++i) {
-            const f2 t = *reinterpret_cast<const f2*>(T + r * Q + 2 * i);
-            y[i] = r == 0 ? f2_muls(t, xr) : f2_fmas(t, xr, y[i]);
-        }
-    }
-}
 
 template <int Q>
 __device__ __forceinline__ void f2_leaf_like(float z, float c2, int q, f2 (&e)[Q / 2]) {

@@ -15,8 +15,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
+#include <vector>
 
-#include "ghm_vec.cuh"
+#include "ghm_vec2.cuh"
 
 #define GD_NT 128
 
@@ -112,9 +114,10 @@ static unsigned lvl_grid(const GhmDev& d, int64_t B, int l) { return (unsigned)(
 
 // ---- BP_CLS, log domain (reference :185-221): nodes of depth l, bottom-up --------------------------
 // node (depth l, idx) of tree b; HD = this tree's compact rows [n_int][q] (global or shared memory)
-template <int Q>
+// EX: q == Q, so the padding predicates (k < q) fold away at compile time
+template <int Q, bool EX>
 __device__ __forceinline__ void cls_node(const GhmDev& d, const LvlArgs& a, int64_t b, int l, int idx, float* HD) {
-    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves;
+    const int L = d.L, s = d.s, q = EX ? Q : d.q, nL = d.n_leaves;
     float acc[Q];
 #pragma unroll
     for (int k = 0; k < Q; ++k) acc[k] = (k < q) ? 0.f : -INFINITY;
@@ -162,14 +165,14 @@ template <int Q>
 __global__ void __launch_bounds__(GD_NT) k_lvl_cls(const GhmDev d, const LvlArgs a, int l) {
     const LvlThread th = lvl_thread(d, a.B, l);
     if (!th.ok) return;
-    cls_node<Q>(d, a, th.b, l, th.idx, a.HD + th.b * (int64_t)a.n_nodes * d.q);
+    cls_node<Q, false>(d, a, th.b, l, th.idx, a.HD + th.b * (int64_t)a.n_nodes * d.q);
 }
 
 // ---- BP_DNS, log domain (reference :467-523): upward pass, nodes of depth l ------------------------
-template <int Q>
+template <int Q, bool EX>
 __device__ __forceinline__ void dns_up_node(const GhmDev& d, const LvlArgs& a, int64_t b, int l, int idx, float* HD, float* QD,
                                             float* BU) {
-    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves;
+    const int L = d.L, s = d.s, q = EX ? Q : d.q, nL = d.n_leaves;
     const int node = node_off_all(d, l) + idx;
     float acc[Q];
     if (l == L) {                                             // leaves: hd unshifted (:485), qd = log(T @ exp(hd)) (:487)
@@ -214,14 +217,14 @@ __global__ void __launch_bounds__(GD_NT) k_lvl_dns_up(const GhmDev d, const LvlA
     const LvlThread th = lvl_thread(d, a.B, l);
     if (!th.ok) return;
     const int64_t base = th.b * (int64_t)a.n_nodes * d.q;
-    dns_up_node<Q>(d, a, th.b, l, th.idx, a.HD + base, a.QD + base, a.BU + base);
+    dns_up_node<Q, false>(d, a, th.b, l, th.idx, a.HD + base, a.QD + base, a.BU + base);
 }
 
 // ---- BP_DNS downward pass: bu = hd + log(T^T @ exp(bu_parent - qd)) - max (:509-514), nodes of depth l >= 1 ----
-template <int Q>
+template <int Q, bool EX>
 __device__ __forceinline__ void dns_down_node(const GhmDev& d, const LvlArgs& a, int64_t b, int l, int idx, float* HD, float* QD,
                                               float* BU) {
-    const int L = d.L, s = d.s, q = d.q, nL = d.n_leaves;
+    const int L = d.L, s = d.s, q = EX ? Q : d.q, nL = d.n_leaves;
     const int node = node_off_all(d, l) + idx;
     const int pidx = ghm_div_s(idx, d);
     const int par = node_off_all(d, l - 1) + pidx;
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(GD_NT) k_lvl_dns_down(const GhmDev d, const Lv
     const LvlThread th = lvl_thread(d, a.B, l);
     if (!th.ok) return;
     const int64_t base = th.b * (int64_t)a.n_nodes * d.q;
-    dns_down_node<Q>(d, a, th.b, l, th.idx, a.HD + base, a.QD + base, a.BU + base);
+    dns_down_node<Q, false>(d, a, th.b, l, th.idx, a.HD + base, a.QD + base, a.BU + base);
 }
 
 // ---- expansion: node messages -> [B, n_L, C] guide tensors ------------------------------------------
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(GD_NT) k_lvl_dns_down(const GhmDev d, const Lv
 // row of tree b in tensor t is n_L * C contiguous floats, written as consecutive 8-byte units by consecutive
 // lanes (fully coalesced); unit u = (leaf i, pair j) reads the float2 (k, k+1) of part j*2/q (hd | qd | bu)
 // of the depth-l ancestor of leaf i from the compact [B][node][q] store (L2 resident, 8-byte aligned for even q).
-#define EXP_MAX_T (2 * GHM_MAX_LEVELS + 1)
+#define EXP_MAX_T GHM_EXP_MAX_T
 struct ExpandT {
     float* out;              // [B][nL][C]
     int level;               // depth of the broadcast nodes
@@ -343,130 +346,358 @@ static int expand_launch(const ExpandAll& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // Tree-tiled fused guide kernels: a CTA owns G consecutive trees, runs the whole log-domain BP level by level on
 // compact message rows held in SHARED memory (no HBM round trip of the node messages, no per-level launches), then
-// streams every guide tensor of its trees -- one contiguous span of G rows per tensor -- as 8-byte units straight
-// from shared memory.  HBM traffic = the inputs + the guide tensors, i.e. the algorithmic bytes.
+// streams every guide tensor of its trees straight from shared memory.  HBM traffic = the inputs + the guide
+// tensors, i.e. the algorithmic bytes.
+//
+// Expansion is table driven: which message element a unit of a tree row copies depends only on (L, s, q), so the
+// model carries one uint16 shared-memory offset per unit (ghm_guides_init).  A thread owns unit u of the row, reads
+// its offset once and copies that unit for each of the CTA's trees: per store one LDS and one STG, no index
+// arithmetic; consecutive lanes write consecutive 8-byte units of a row (fully coalesced).
 // ------------------------------------------------------------------------------------------------
-#define GF_NT 128
+// Levels near the root keep only the first warp(s) of a CTA busy, and warp w of every CTA lives on scheduler w % 4:
+// rotate the thread -> work-item mapping by (CTA, level) so those single-warp rounds spread over the four schedulers.
+__device__ __forceinline__ int rot_tid(int l) {
+    const int nw = blockDim.x >> 5;
+    int t = (int)threadIdx.x + 32 * (int)((blockIdx.x + (unsigned)l) % (unsigned)nw);
+    return t >= (int)blockDim.x ? t - (int)blockDim.x : t;
+}
+
+#define GF_NT 256                                            // launch bound; the block size is a launch parameter
+#define GF_NT_CLS 128                                        // measured best: 128 threads for the cls set, 256 for the dns set
+#define GF_NT_DNS 256
+struct FusedExp {
+    const uint16_t* tab;
+    int n_t, stride;
+    int tab_off[GHM_EXP_MAX_T];
+    int upt[GHM_EXP_MAX_T];
+    float* out[GHM_EXP_MAX_T];
+};
+
+#define GF_CH 8                                              // table entries a thread holds per chunk
 template <bool VEC2>
-__device__ __forceinline__ void expand_from_smem(const ExpandAll& e, const float* s0, const float* s1, const float* s2,
-                                                 int tree_stride, int64_t tree0, int g) {
-    const int q = e.q, W = VEC2 ? 2 : 1;
-    const int hq = q / W;
-    const int ncell = g * e.nL;                               // leaf cells of this CTA's trees, contiguous per tensor
-    const unsigned nL_magic = e.nL >= 2 ? (unsigned)((0x100000000ull + (unsigned)e.nL - 1) / (unsigned)e.nL) : 0u;
-    for (int ti = 0; ti < e.n_t; ++ti) {
-        const ExpandT& t = e.t[ti];
-        const int C2 = t.nsrc * hq;                           // 8-byte units per cell
-        // threads = [cells per iteration][unit within the cell]: the unit's (part, k) is fixed per thread for the whole
-        // tensor and only the cell advances, so the per-store index work is two multiply-high divisions
-        if (C2 < 8) {                                         // narrow cells (cls guides): flat unit index, three divisions
-            const int upt = e.nL * C2, total = g * upt;
-            const unsigned C2_magic = C2 >= 2 ? (unsigned)((0x100000000ull + (unsigned)C2 - 1) / (unsigned)C2) : 0u;
-            const unsigned upt_magic = upt >= 2 ? (unsigned)((0x100000000ull + (unsigned)upt - 1) / (unsigned)upt) : 0u;
-            const float* p0 = t.src[0] == 0 ? s0 : (t.src[0] == 1 ? s1 : s2);
-            const int R0 = e.R[t.level]; const unsigned Rm0 = e.R_magic[t.level];
-            const int noff0 = e.node_off[t.level];
-            float* o = t.out + tree0 * (int64_t)upt * W;
-#pragma unroll 4
-            for (int u = threadIdx.x; u < total; u += GF_NT) {
-                const int tr = div_magic(u, upt, upt_magic);
-                const int ul = u - tr * upt;
-                const int i = div_magic(ul, C2, C2_magic);
-                const int jj = ul - i * C2;
-                const int part = (jj >= hq) + (jj >= 2 * hq);
-                const int kk = jj - part * hq;
-                const float* pb = part == 0 ? p0 : (t.src[part] == 0 ? s0 : (t.src[part] == 1 ? s1 : s2));
-                const float* src = pb + tr * tree_stride + (noff0 + div_magic(i, R0, Rm0)) * q + kk * W;
-                if (VEC2) reinterpret_cast<float2*>(o)[u] = *reinterpret_cast<const float2*>(src);
-                else o[u] = *src;
+__device__ __forceinline__ void expand_tab(const FusedExp& e, const float* gsm, int64_t tree0, int g) {
+    typedef typename std::conditional<VEC2, float2, float>::type U;
+    const int stride = e.stride, NT = blockDim.x;
+    // work list = (tensor, chunk of GF_CH * GF_NT units).  Global loads queue behind the stores already in the
+    // memory pipe, so the offsets of the NEXT chunk are fetched before the stores of the current one are issued.
+    auto fetch = [&](int ti, int base, unsigned (&o)[GF_CH]) {
+        const uint16_t* __restrict__ tab = e.tab + e.tab_off[ti] + base + threadIdx.x;
+        const int left = e.upt[ti] - base - (int)threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < GF_CH; ++k) o[k] = (k * NT < left) ? (unsigned)__ldg(tab + k * NT) : 0u;
+    };
+    unsigned cur[GF_CH], nxt[GF_CH];
+    int ti = 0, base = 0;
+    if (e.n_t > 0) fetch(0, 0, cur);
+    while (ti < e.n_t) {
+        const int upt = e.upt[ti];
+        int nti = ti, nbase = base + GF_CH * NT;
+        if (nbase >= upt) { ++nti; nbase = 0; }
+        if (nti < e.n_t) fetch(nti, nbase, nxt);
+        U* __restrict__ out = reinterpret_cast<U*>(e.out[ti]) + tree0 * upt + base + threadIdx.x;
+        const int left = upt - base - (int)threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < GF_CH; ++k) {
+            if (k * NT < left) {
+                const float* sp = gsm + cur[k];
+                U* o = out + k * NT;
+                int tr = 0;
+                for (; tr + 4 <= g; tr += 4) {
+                    const U v0 = *reinterpret_cast<const U*>(sp + (tr + 0) * stride);
+                    const U v1 = *reinterpret_cast<const U*>(sp + (tr + 1) * stride);
+                    const U v2 = *reinterpret_cast<const U*>(sp + (tr + 2) * stride);
+                    const U v3 = *reinterpret_cast<const U*>(sp + (tr + 3) * stride);
+                    o[(size_t)(tr + 0) * upt] = v0;
+                    o[(size_t)(tr + 1) * upt] = v1;
+                    o[(size_t)(tr + 2) * upt] = v2;
+                    o[(size_t)(tr + 3) * upt] = v3;
+                }
+                for (; tr < g; ++tr) o[(size_t)tr * upt] = *reinterpret_cast<const U*>(sp + tr * stride);
             }
-            continue;
         }
-        const int cpi = GF_NT / C2;                           // >= 1 (C2 <= 3*q/2 <= 24)
-        const int cell0 = (int)threadIdx.x / C2, j = (int)threadIdx.x - cell0 * C2;
-        if (cell0 >= cpi) continue;                           // the few lanes past the last whole cell idle
-        const int part = (j >= hq) + (j >= 2 * hq);
-        const int kk = j - part * hq;
-        const float* pp = t.src[part] == 0 ? s0 : (t.src[part] == 1 ? s1 : s2);
-        pp += kk * W;
-        const int R = e.R[t.level]; const unsigned Rm = e.R_magic[t.level];
-        const int noff = e.node_off[t.level];
-        float* out = t.out + (tree0 * e.nL) * (int64_t)C2 * W + j * W;
-#pragma unroll 4
-        for (int cell = cell0; cell < ncell; cell += cpi) {
-            const int tr = div_magic(cell, e.nL, nL_magic);
-            const int i = cell - tr * e.nL;
-            const int node = noff + div_magic(i, R, Rm);
-            const float* src = pp + tr * tree_stride + node * q;
-            if (VEC2) *reinterpret_cast<float2*>(out + (size_t)cell * C2 * W) = *reinterpret_cast<const float2*>(src);
-            else out[(size_t)cell * C2] = *src;
-        }
+#pragma unroll
+        for (int k = 0; k < GF_CH; ++k) cur[k] = nxt[k];
+        ti = nti; base = nbase;
     }
 }
 
-template <int Q, bool VEC2>
-__global__ void __launch_bounds__(GF_NT) k_guides_dns_fused(const GhmDev d, const LvlArgs a, const __grid_constant__ ExpandAll e,
+template <int Q, bool EX, bool VEC2>
+__global__ void __launch_bounds__(GF_NT) k_guides_dns_fused(const GhmDev d, const LvlArgs a, const __grid_constant__ FusedExp e,
                                                             int G) {
     extern __shared__ __align__(16) float gsm[];
-    const int q = d.q, L = d.L;
-    const int stride = a.n_nodes * q;                       // floats per tree per array
+    const int L = d.L;
+    const int stride = e.stride;                            // floats per tree per array
     float* HD = gsm; float* QD = HD + (size_t)G * stride; float* BU = QD + (size_t)G * stride;
     const int64_t tree0 = (int64_t)blockIdx.x * G;
     const int g = (int)min((int64_t)G, a.B - tree0);
     for (int l = L; l >= 0; --l) {
         const int n = d.spow[l];
-        const unsigned nm = n >= 2 ? (unsigned)((0x100000000ull + (unsigned)n - 1) / (unsigned)n) : 0u;
-        for (int w = threadIdx.x; w < g * n; w += GF_NT) {
+        const unsigned nm = d.pow_magic[l];                 // ceil(2^32 / s^l), host-computed
+        for (int w = rot_tid(l); w < g * n; w += blockDim.x) {
             const int t = div_magic(w, n, nm), idx = w - t * n;
-            dns_up_node<Q>(d, a, tree0 + t, l, idx, HD + t * stride, QD + t * stride, BU + t * stride);
+            dns_up_node<Q, EX>(d, a, tree0 + t, l, idx, HD + t * stride, QD + t * stride, BU + t * stride);
         }
         __syncthreads();
     }
     for (int l = 1; l <= L; ++l) {
         const int n = d.spow[l];
-        const unsigned nm = n >= 2 ? (unsigned)((0x100000000ull + (unsigned)n - 1) / (unsigned)n) : 0u;
-        for (int w = threadIdx.x; w < g * n; w += GF_NT) {
+        const unsigned nm = d.pow_magic[l];                 // ceil(2^32 / s^l), host-computed
+        for (int w = rot_tid(l); w < g * n; w += blockDim.x) {
             const int t = div_magic(w, n, nm), idx = w - t * n;
-            dns_down_node<Q>(d, a, tree0 + t, l, idx, HD + t * stride, QD + t * stride, BU + t * stride);
+            dns_down_node<Q, EX>(d, a, tree0 + t, l, idx, HD + t * stride, QD + t * stride, BU + t * stride);
         }
         __syncthreads();
     }
-    expand_from_smem<VEC2>(e, HD, QD, BU, stride, tree0, g);
+    expand_tab<VEC2>(e, gsm, tree0, g);
 }
 
-template <int Q, bool VEC2>
-__global__ void __launch_bounds__(GF_NT) k_guides_cls_fused(const GhmDev d, const LvlArgs a, const __grid_constant__ ExpandAll e,
+// ---- packed / constant-bank variant of the fused dns kernel (translation-invariant tables, q == Q) ----------------
+// One thread per PARENT node, looping over its s children: the matrix of child c is the same for every thread of
+// the CTA, so its index is a uniform loop counter and the Q*Q/2 packed FMAs of a matvec read the table from the
+// constant bank through uniform registers -- no LSU traffic for the tables, which otherwise queues behind the
+// guide-tensor stores of the co-resident CTAs (that queueing made BP and expansion time add up instead of overlap).
+struct GuideC { int up_base, dn_off, s_u; };               // uniform-side twins: (L-1)*s, float offset of Tlin, s
+
+template <int H>
+__device__ __forceinline__ void f2_ld(const float* p, f2 (&v)[H]) {
+#pragma unroll
+    for (int i = 0; i < H; ++i) v[i] = reinterpret_cast<const f2*>(p)[i];
+}
+template <int H>
+__device__ __forceinline__ void f2_st(float* p, const f2 (&v)[H]) {
+#pragma unroll
+    for (int i = 0; i < H; ++i) reinterpret_cast<f2*>(p)[i] = v[i];
+}
+template <int H>
+__device__ __forceinline__ float f2_vmax(const f2 (&v)[H]) {
+    float m = fmaxf(v[0].x, v[0].y);
+#pragma unroll
+    for (int i = 1; i < H; ++i) m = fmaxf(m, fmaxf(v[i].x, v[i].y));
+    return m;
+}
+// out = log(M @ exp(h - max h)) + max h, M = the Q x Q table at T (constant bank, see f2_matvec_c)
+template <int Q>
+__device__ __forceinline__ void f2_log_matvec_c(const float* __restrict__ T, const f2 (&h)[Q / 2], f2 (&out)[Q / 2]) {
+    const float m = f2_vmax<Q / 2>(h);
+    f2 e[Q / 2], u[Q / 2];
+#pragma unroll
+    for (int i = 0; i < Q / 2; ++i) e[i] = make_float2(__expf(h[i].x - m), __expf(h[i].y - m));
+    f2_matvec_c<Q>(T, e, u);
+#pragma unroll
+    for (int i = 0; i < Q / 2; ++i) out[i] = make_float2(__logf(u[i].x) + m, __logf(u[i].y) + m);
+}
+
+template <int Q, bool VEC2, int NW>
+__global__ void __launch_bounds__(GF_NT)
+k_guides_dns_fused_c(const __grid_constant__ GhmDev d, const __grid_constant__ LvlArgs a, const __grid_constant__ FusedExp e,
+                     const __grid_constant__ GuideC gc, int G, const __grid_constant__ DnsTab<NW> tab) {
+    extern __shared__ __align__(16) float gsm[];
+    constexpr int H = Q / 2, QQ = Q * Q;
+    const int L = d.L, s = d.s, nL = d.n_leaves;
+    const int stride = e.stride, NT = blockDim.x, tid = threadIdx.x;
+    float* HD = gsm; float* QD = HD + (size_t)G * stride; float* BU = QD + (size_t)G * stride;
+    const int64_t tree0 = (int64_t)blockIdx.x * G;
+    const int g = (int)min((int64_t)G, a.B - tree0);
+    const float* Tup = tab.v;
+    const float* Tdn = tab.v + gc.dn_off;
+    const float inv2s2 = 0.5f / (a.sigma * a.sigma);
+    // the CTA's noisy leaves, one coalesced read, parked in the BU region (first written at the root of the up pass,
+    // after the leaf level has consumed them)
+    float* zs = BU;
+    for (int i = tid; i < g * nL; i += NT) zs[i] = a.z[tree0 * nL + i];
+    __syncthreads();
+    // upward pass (reference :483-506): parents of depth l = L-1 .. 0
+    int tmb = gc.up_base;
+    for (int l = L - 1; l >= 0; --l, tmb -= gc.s_u) {
+        const int n = d.spow[l], items = g * n;
+        const unsigned nm = d.pow_magic[l];                 // ceil(2^32 / s^l), host-computed
+        const int noff_c = 1 + d.edge_off[l + 1], noff_p = l == 0 ? 0 : 1 + d.edge_off[l];
+        const int rt = rot_tid(l);
+        for (int w0 = 0; w0 < items; w0 += NT) {                // uniform trip count; the tail is predicated
+            const bool act = w0 + rt < items;
+            if (!__any_sync(0xffffffffu, act)) continue;        // warp-uniform skip (vote results stay on the uniform side)
+            const int w = act ? w0 + rt : items - 1;
+            const int t = div_magic(w, n, nm), idx = w - t * n;
+            float* hd = HD + t * stride; float* qd = QD + t * stride;
+            f2 acc[H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) acc[i] = make_float2(0.f, 0.f);
+            int tm = tmb;
+#pragma unroll 1
+            for (int c = 0; c < s; ++c, ++tm) {
+                const int ci = idx * s + c;
+                f2 h[H], m[H];
+                if (l == L - 1) {                               // leaf hd, unshifted (:485)
+                    const float zi = zs[t * nL + ci];
+#pragma unroll
+                    for (int i = 0; i < H; ++i) {
+                        const float da = zi - (float)(2 * i), db = zi - (float)(2 * i + 1);
+                        h[i] = make_float2(-da * da * inv2s2, -db * db * inv2s2);
+                    }
+                    if (act) f2_st<H>(hd + (noff_c + ci) * Q, h);
+                } else {
+                    f2_ld<H>(hd + (noff_c + ci) * Q, h);
+                }
+                f2_log_matvec_c<Q>(Tup + tm * QQ, h, m);        // qd = log(T @ exp(hd)) (:487,497)
+                if (act) f2_st<H>(qd + (noff_c + ci) * Q, m);
+#pragma unroll
+                for (int i = 0; i < H; ++i) { acc[i].x += m[i].x; acc[i].y += m[i].y; }
+            }
+            const float mx = f2_vmax<H>(acc);                   // hd = sum qd(children) - max (:494-496)
+#pragma unroll
+            for (int i = 0; i < H; ++i) { acc[i].x -= mx; acc[i].y -= mx; }
+            if (l > 0) {
+                if (act) f2_st<H>(hd + (noff_p + idx) * Q, acc);
+            } else {                                            // root: bu aliases hd, external message unshifted (:501-506)
+                if (a.ext) {
+                    f2 x[H];
+                    f2_ld<H>(a.ext + (tree0 + t) * Q, x);
+#pragma unroll
+                    for (int i = 0; i < H; ++i) { acc[i].x += x[i].x; acc[i].y += x[i].y; }
+                }
+                if (act) { f2_st<H>(hd, acc); f2_st<H>(BU + t * stride, acc); }
+            }
+        }
+        __syncthreads();
+    }
+    // downward pass (:509-519): children of the depth-l parents
+    int tmd = 0;
+    for (int l = 0; l < L; ++l, tmd += gc.s_u) {
+        const int n = d.spow[l], items = g * n;
+        const unsigned nm = d.pow_magic[l];                 // ceil(2^32 / s^l), host-computed
+        const int noff_c = 1 + d.edge_off[l + 1], noff_p = l == 0 ? 0 : 1 + d.edge_off[l];
+        const int rt = rot_tid(l + 1);
+        for (int w0 = 0; w0 < items; w0 += NT) {
+            const bool act = w0 + rt < items;
+            if (!__any_sync(0xffffffffu, act)) continue;        // warp-uniform skip (vote results stay on the uniform side)
+            const int w = act ? w0 + rt : items - 1;
+            const int t = div_magic(w, n, nm), idx = w - t * n;
+            float* hd = HD + t * stride; float* qd = QD + t * stride; float* bu = BU + t * stride;
+            f2 bp[H];
+            f2_ld<H>(bu + (noff_p + idx) * Q, bp);
+            int tm = tmd;
+#pragma unroll 1
+            for (int c = 0; c < s; ++c, ++tm) {
+                const int ci = idx * s + c, node = noff_c + ci;
+                f2 qv[H], hv[H], m[H];
+                f2_ld<H>(qd + node * Q, qv);
+                f2_ld<H>(hd + node * Q, hv);
+#pragma unroll
+                for (int i = 0; i < H; ++i) { qv[i].x = bp[i].x - qv[i].x; qv[i].y = bp[i].y - qv[i].y; }
+                f2_log_matvec_c<Q>(Tdn + tm * QQ, qv, m);
+#pragma unroll
+                for (int i = 0; i < H; ++i) { m[i].x += hv[i].x; m[i].y += hv[i].y; }
+                const float mx = f2_vmax<H>(m);
+#pragma unroll
+                for (int i = 0; i < H; ++i) { m[i].x -= mx; m[i].y -= mx; }
+                if (act) f2_st<H>(bu + node * Q, m);
+                if (l == L - 1 && a.mean) {
+                    float num = 0.f, den = 0.f;
+#pragma unroll
+                    for (int i = 0; i < H; ++i) {
+                        const float ea = __expf(m[i].x), eb = __expf(m[i].y);
+                        num += (float)(2 * i) * ea + (float)(2 * i + 1) * eb; den += ea + eb;
+                    }
+                    if (act) a.mean[(tree0 + t) * nL + ci] = __fdividef(num, den);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    expand_tab<VEC2>(e, gsm, tree0, g);
+}
+
+template <int Q, bool EX, bool VEC2>
+__global__ void __launch_bounds__(GF_NT) k_guides_cls_fused(const GhmDev d, const LvlArgs a, const __grid_constant__ FusedExp e,
                                                             int G) {
     extern __shared__ __align__(16) float gsm[];
-    const int q = d.q, L = d.L;
-    const int stride = a.n_nodes * q;
+    const int L = d.L;
+    const int stride = e.stride;
     float* HD = gsm;
     const int64_t tree0 = (int64_t)blockIdx.x * G;
     const int g = (int)min((int64_t)G, a.B - tree0);
     for (int l = L - 1; l >= 0; --l) {
         const int n = d.spow[l];
-        const unsigned nm = n >= 2 ? (unsigned)((0x100000000ull + (unsigned)n - 1) / (unsigned)n) : 0u;
-        for (int w = threadIdx.x; w < g * n; w += GF_NT) {
+        const unsigned nm = d.pow_magic[l];                 // ceil(2^32 / s^l), host-computed
+        for (int w = rot_tid(l); w < g * n; w += blockDim.x) {
             const int t = div_magic(w, n, nm), idx = w - t * n;
-            cls_node<Q>(d, a, tree0 + t, l, idx, HD + t * stride);
+            cls_node<Q, EX>(d, a, tree0 + t, l, idx, HD + t * stride);
         }
         __syncthreads();
     }
-    expand_from_smem<VEC2>(e, HD, HD, HD, stride, tree0, g);
+    expand_tab<VEC2>(e, gsm, tree0, g);
 }
 
 // trees per CTA of the fused kernels for `arrays` compact arrays; 0 -> does not fit, use the level kernels
-static int fused_trees_per_cta(int n_nodes, int q, int arrays) {
+static int fused_trees_per_cta(int64_t n_nodes, int q, int arrays) {
     const size_t per_tree = (size_t)arrays * n_nodes * q * sizeof(float);
     const size_t budget = 70 * 1024;                        // 3 CTAs per SM
     int G = (int)(budget / per_tree);
     return G > 16 ? 16 : G;
 }
 
-static bool expand_vec2(const ExpandAll& a) {
-    bool vec2 = (a.q % 2) == 0;
-    for (int i = 0; i < a.n_t; ++i) vec2 = vec2 && ((uintptr_t)a.t[i].out % 8) == 0;
-    return vec2;
+static int64_t n_nodes_all(const GhmDev& d) { return 1 + (int64_t)d.n_edges; }
+static int64_t n_nodes_int(const GhmDev& d) { return 1 + (int64_t)d.edge_off[d.L]; }   // depths 0..L-1
+
+// offsets of one tensor: unit u = (leaf i, part, k) -> float offset of SRC_part[node(level, i / s^(L-level))][k] in a CTA's
+// shared memory, where array `a` of tree 0 starts at a * G * stride
+static void tab_add(std::vector<uint16_t>& tab, GhmGuideTab& gt, const GhmDev& d, int level, int nsrc, int p0, int p1, int p2) {
+    const int W = gt.W, hq = d.q / W, C2 = nsrc * hq, nL = d.n_leaves;
+    const int R = d.spow[d.L - level], noff = level == 0 ? 0 : 1 + d.edge_off[level];
+    const int part_arr[3] = {p0, p1, p2};
+    gt.tab_off[gt.n_t] = (int)tab.size();
+    gt.upt[gt.n_t] = nL * C2;
+    ++gt.n_t;
+    for (int i = 0; i < nL; ++i)
+        for (int j = 0; j < C2; ++j) {
+            const int part = j / hq, kk = j - part * hq;
+            tab.push_back((uint16_t)((size_t)part_arr[part] * gt.G * gt.stride + (size_t)(noff + i / R) * d.q + kk * W));
+        }
+}
+
+int ghm_guides_init(ghm_model* m) {
+    const GhmDev& d = m->d;
+    m->gt_cls = GhmGuideTab{}; m->gt_dns = GhmGuideTab{};
+    if (d.q > GHM_MAX_Q_REG || d.s < 2) return GHM_OK;
+    std::vector<uint16_t> tab;
+    const int L = d.L, W = (d.q % 2 == 0) ? 2 : 1;
+    {   // cls set: guides[j] <- hd of depth L-1-j     (reference :533-549)
+        GhmGuideTab& gt = m->gt_cls;
+        gt.W = W; gt.stride = (int)(n_nodes_int(d) * d.q);
+        gt.G = fused_trees_per_cta(n_nodes_int(d), d.q, 1);
+        if (gt.G >= 1)
+            for (int j = 0; j < L; ++j) tab_add(tab, gt, d, L - 1 - j, 1, 0, 0, 0);
+    }
+    {   // dns set: (hd|qd) depth L..1 ; root (hd|bu) ; (hd|qd|bu) depth 1..L      (reference :554-590)
+        GhmGuideTab& gt = m->gt_dns;
+        gt.W = W; gt.stride = (int)(n_nodes_all(d) * d.q);
+        gt.G = fused_trees_per_cta(n_nodes_all(d), d.q, 3);
+        if (gt.G >= 1) {
+            for (int j = 0; j < L; ++j) tab_add(tab, gt, d, L - j, 2, 0, 1, 0);
+            tab_add(tab, gt, d, 0, 2, 0, 2, 0);
+            for (int j = 1; j <= L; ++j) tab_add(tab, gt, d, j, 3, 0, 1, 2);
+        }
+    }
+    if (tab.empty()) return GHM_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (prev != m->device) cudaSetDevice(m->device);
+    cudaError_t ce = cudaMalloc(&m->guide_tab, tab.size() * sizeof(uint16_t));
+    if (ce == cudaSuccess) ce = cudaMemcpy(m->guide_tab, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+    if (prev != m->device) cudaSetDevice(prev);
+    if (ce != cudaSuccess) return ghm_fail(GHM_ECUDA, "guide offset tables: %s", cudaGetErrorString(ce));
+    return GHM_OK;
+}
+
+// fused launch descriptor for one call; false when an output pointer rules the fused kernel out
+static bool fused_setup(FusedExp& e, const ghm_model* m, const GhmGuideTab& gt, float* const* guides) {
+    if (gt.G < 1 || !m->guide_tab) return false;
+    e.tab = m->guide_tab; e.n_t = gt.n_t; e.stride = gt.stride;
+    for (int i = 0; i < gt.n_t; ++i) {
+        e.tab_off[i] = gt.tab_off[i]; e.upt[i] = gt.upt[i]; e.out[i] = guides[i];
+        if (!guides[i] || (gt.W == 2 && ((uintptr_t)guides[i] % 8) != 0)) return false;
+    }
+    return true;
 }
 
 template <typename F>
@@ -487,9 +718,6 @@ struct DevGuard {
     explicit DevGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
     ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
-
-static int64_t n_nodes_all(const GhmDev& d) { return 1 + (int64_t)d.n_edges; }
-static int64_t n_nodes_int(const GhmDev& d) { return 1 + (int64_t)d.edge_off[d.L]; }   // depths 0..L-1
 
 // ---- cls guides ------------------------------------------------------------------------------------
 // workspace: HD [B][n_int][q] f32 -- carried in the LAST guide tensor's tail?  No: guides[L-1] is the
@@ -515,25 +743,22 @@ extern "C" int ghm_guides_cls(const ghm_model_t* m, int64_t B, const void* leave
     LvlArgs a{};
     a.B = B; a.leaves = leaves; a.leaf_dtype = leaf_dtype; a.n_nodes = (int)n_int;
     a.post = post; a.root_hd = root_hd;
-    const int G = fused_trees_per_cta((int)n_int, d.q, 1);
-    if (G >= 1) {                                              // tree-tiled fused kernel: messages never leave shared memory
-        ExpandAll e;
-        expand_setup(e, d, B, (int)n_int, nullptr, nullptr, nullptr);
-        for (int j = 0; j < L; ++j) expand_add(e, guides[j], L - 1 - j, 1, 0, 0, 0);
+    FusedExp fe;
+    if (fused_setup(fe, m, m->gt_cls, guides)) {               // tree-tiled fused kernel: messages never leave shared memory
+        const int G = m->gt_cls.G;
         const size_t dyn = (size_t)G * n_int * d.q * sizeof(float);
         const unsigned grid = (unsigned)((B + G - 1) / G);
-        const bool v2 = expand_vec2(e);
+        const bool v2 = m->gt_cls.W == 2;
         return dispatch_q(d.q, [&](auto Qc) -> int {
             constexpr int Q = decltype(Qc)::value;
-            if (v2) {
-                GHM_CUDA_TRY(cudaFuncSetAttribute(k_guides_cls_fused<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                k_guides_cls_fused<Q, true><<<grid, GF_NT, dyn, st>>>(d, a, e, G);
-            } else {
-                GHM_CUDA_TRY(cudaFuncSetAttribute(k_guides_cls_fused<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                k_guides_cls_fused<Q, false><<<grid, GF_NT, dyn, st>>>(d, a, e, G);
-            }
-            GHM_CHECK_LAUNCH();
-            return GHM_OK;
+            auto go = [&](auto kern) -> int {
+                GHM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                kern<<<grid, GF_NT_CLS, dyn, st>>>(d, a, fe, G);
+                GHM_CHECK_LAUNCH();
+                return GHM_OK;
+            };
+            if (d.q == Q) return v2 ? go(k_guides_cls_fused<Q, true, true>) : go(k_guides_cls_fused<Q, true, false>);
+            return v2 ? go(k_guides_cls_fused<Q, false, true>) : go(k_guides_cls_fused<Q, false, false>);
         });
     }
     // large trees: level kernels on a compact store staged inside the root guide tensor, expanded last
@@ -588,27 +813,37 @@ extern "C" int ghm_guides_dns(const ghm_model_t* m, int64_t B, const float* z, f
     float* BU = QD + B * nn * d.q;
     LvlArgs a{};
     a.B = B; a.z = z; a.sigma = sigma; a.ext = ext; a.HD = HD; a.QD = QD; a.BU = BU; a.n_nodes = (int)nn; a.mean = mean;
-    const int G = guides ? fused_trees_per_cta((int)nn, d.q, 3) : 0;
-    if (G >= 1) {                                              // tree-tiled fused kernel: messages never leave shared memory
-        ExpandAll e;
-        expand_setup(e, d, B, (int)nn, nullptr, nullptr, nullptr);
-        for (int j = 0; j < L; ++j) expand_add(e, guides[j], L - j, 2, 0, 1, 0);
-        expand_add(e, guides[L], 0, 2, 0, 2, 0);
-        for (int j = 1; j <= L; ++j) expand_add(e, guides[L + j], j, 3, 0, 1, 2);
+    FusedExp fe;
+    if (guides && fused_setup(fe, m, m->gt_dns, guides)) {     // tree-tiled fused kernel: messages never leave shared memory
+        const int G = m->gt_dns.G;
         const size_t dyn = (size_t)3 * G * nn * d.q * sizeof(float);
         const unsigned grid = (unsigned)((B + G - 1) / G);
-        const bool v2 = expand_vec2(e);
+        const bool v2 = m->gt_dns.W == 2;
         return dispatch_q(d.q, [&](auto Qc) -> int {
             constexpr int Q = decltype(Qc)::value;
-            if (v2) {
-                GHM_CUDA_TRY(cudaFuncSetAttribute(k_guides_dns_fused<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                k_guides_dns_fused<Q, true><<<grid, GF_NT, dyn, st>>>(d, a, e, G);
-            } else {
-                GHM_CUDA_TRY(cudaFuncSetAttribute(k_guides_dns_fused<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                k_guides_dns_fused<Q, false><<<grid, GF_NT, dyn, st>>>(d, a, e, G);
+            const size_t words = (size_t)d.n_mat * Q * Q;
+            if (d.ti && d.q == Q && 2 * words <= (size_t)GHM_TAB_WORDS) {
+                GuideC gc{(d.L - 1) * d.s, (int)words, d.s};
+                DnsTab<GHM_TAB_WORDS> tab;
+                tab.v[0] = 0.f;
+                memcpy(tab.v, m->h_TlinT, words * sizeof(float));
+                memcpy(tab.v + words, m->h_Tlin, words * sizeof(float));
+                auto goc = [&](auto kern) -> int {
+                    GHM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                    kern<<<grid, GF_NT_DNS, dyn, st>>>(d, a, fe, gc, G, tab);
+                    GHM_CHECK_LAUNCH();
+                    return GHM_OK;
+                };
+                return v2 ? goc(k_guides_dns_fused_c<Q, true, GHM_TAB_WORDS>) : goc(k_guides_dns_fused_c<Q, false, GHM_TAB_WORDS>);
             }
-            GHM_CHECK_LAUNCH();
-            return GHM_OK;
+            auto go = [&](auto kern) -> int {
+                GHM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                kern<<<grid, GF_NT_DNS, dyn, st>>>(d, a, fe, G);
+                GHM_CHECK_LAUNCH();
+                return GHM_OK;
+            };
+            if (d.q == Q) return v2 ? go(k_guides_dns_fused<Q, true, true>) : go(k_guides_dns_fused<Q, true, false>);
+            return v2 ? go(k_guides_dns_fused<Q, false, true>) : go(k_guides_dns_fused<Q, false, false>);
         });
     }
     int rc = dispatch_q(d.q, [&](auto Qc) -> int {

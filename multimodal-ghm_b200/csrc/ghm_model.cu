@@ -214,6 +214,8 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     m->h_TTp = (float*)((char*)m->h_slab + o.TTp);
     m->h_Tlin = (float*)((char*)m->h_slab + o.Tlin);
     m->h_TlinT = (float*)((char*)m->h_slab + o.TlinT);
+    rc = ghm_guides_init(m);
+    if (rc) { ghm_model_destroy(m); return rc; }
     *out = m;
     return GHM_OK;
 }
@@ -255,6 +257,7 @@ extern "C" int ghm_model_destroy(ghm_model_t* m) {
     if (m->stream) cudaStreamDestroy(m->stream);
     if (m->upload_done) cudaEventDestroy(m->upload_done);
     if (m->slab) cudaFree(m->slab);
+    if (m->guide_tab) cudaFree(m->guide_tab);
     if (m->h_slab) cudaFreeHost(m->h_slab);
     if (m->d_scratch) cudaFree(m->d_scratch);
     if (m->h_scratch) cudaFreeHost(m->h_scratch);

@@ -107,3 +107,25 @@ __device__ __forceinline__ void f2_matvec_up1(const float* __restrict__ TT, cons
         for (int i = 0; i < Q / 2; ++i) y0[i] = b == 0 ? f2_muls(row[i], xb0) : f2_fmas(row[i], xb0, y0[i]);
     }
 }
+
+// ---- transition tables as a by-value kernel parameter (constant bank) ------------------------------------------
+// [0, n_mat*Q*Q): TlinT (child->parent matvec) | [n_mat*Q*Q, 2*n_mat*Q*Q): Tlin (parent->child matvec).  With a
+// warp-uniform matrix index the packed FMAs take their table operand from uniform registers (LDCU), i.e. the matvec
+// issues no LSU instruction at all.
+template <int NW>
+struct __align__(16) DnsTab { float v[NW]; };
+#define GHM_TAB_WORDS 6144
+
+// y[i] = sum_r T[r][2i..2i+1] * x[r]  with T rows of Q floats (8-byte aligned), table in the constant bank
+template <int Q>
+__device__ __forceinline__ void f2_matvec_c(const float* __restrict__ T, const f2 (&x)[Q / 2], f2 (&y)[Q / 2]) {
+#pragma unroll
+    for (int r = 0; r < Q; ++r) {
+        const float xr = f2_elem<Q>(x, r);
+#pragma unroll
+        for (int i = 0; i < Q / 2; ++i) {
+            const f2 t = *reinterpret_cast<const f2*>(T + r * Q + 2 * i);
+            y[i] = r == 0 ? f2_muls(t, xr) : f2_fmas(t, xr, y[i]);
+        }
+    }
+}
