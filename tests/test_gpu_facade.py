@@ -247,3 +247,40 @@ def test_reference_unit_tests_run_against_facade(G):
     sampler = G.DenoiseSampler(3, 3, u10, 0.1, flip_scale=1, sigma=0.1, translation_invariance=True, variable_type=10)
     res = sampler.get_batch(batch_size=10000, guide=True)
     assert denoise_test(res[1], res[-1]) < 3e-3
+
+
+def test_ood_sweeps_reproduce_reference_columns(kat):
+    """ghm_b200.sweeps (device-resident p_flip sweeps, one D2H copy at the end) against the reference's own
+    ood-clip.json / vlm-ood.json columns at grid points 2, 4, 20 and 40 % (figures/eval-clip-ood.py:69-94,
+    eval-vlm-ood.py:104-132)."""
+    from ghm_b200 import sweeps
+    pts = [2, 4, 20, 40]
+    idx = [p // 2 - 1 for p in pts]
+    res = sweeps.clip_ood_sweep(pts, n_eval=10000, batch_size=5000)
+    assert res["p_flip"] == pts
+    for j, i in enumerate(idx):
+        assert res["Bayes"][j] == pytest.approx(kat["ood-clip.json"]["Bayes"][i], rel=1e-5)
+        assert res["Mis-spec. BP"][j] == pytest.approx(kat["ood-clip.json"]["Mis-spec. BP"][i], rel=1e-5)
+    res = sweeps.vlm_ood_sweep(pts, n_eval=10000, batch_size=1000)
+    for j, i in enumerate(idx):
+        assert res["Bayes"][j] == pytest.approx(kat["vlm-ood.json"]["Bayes"][i], rel=1e-5)
+        assert res["Mis-spec. BP"][j] == pytest.approx(kat["vlm-ood.json"]["Mis-spec. BP"][i], rel=1e-5)
+
+
+def test_ood_sweeps_philox_consistency(tmp_path):
+    """Philox mode: at p == p_model the mis-specified BP *is* the Bayes rule, so the two columns agree within their
+    sampling error; away from it the mis-specified risk is larger; the JSON written is the reference's layout."""
+    from ghm_b200 import sweeps
+    res = sweeps.clip_ood_sweep([10, 20, 30], n_eval=40000, batch_size=40000, rng="philox", seed=11)
+    se = res["Bayes SE"]
+    assert abs(res["Mis-spec. BP"][1] - res["Bayes"][1]) < 6 * se[1]
+    for k in (0, 2):                                       # no rule beats the Bayes rule (two independent estimates)
+        assert res["Mis-spec. BP"][k] > res["Bayes"][k] - 6 * se[k]
+    assert res["Mis-spec. BP"][2] > res["Bayes"][2]
+    res_c = sweeps.cdm_ood_sweep([20, 30], n_eval=20000, batch_size=20000, rng="philox", seed=3)
+    assert abs(res_c["Mis-spec. BP"][0] - res_c["Bayes"][0]) < 6 * res_c["Bayes SE"][0]
+    assert res_c["Mis-spec. BP"][1] > res_c["Bayes"][1]
+    out = sweeps.write_reference_json(res, tmp_path / "clip-ood.json", extra={"Standard TF": [1.0, 2.0, 3.0]})
+    back = json.load(open(tmp_path / "clip-ood.json"))
+    assert list(back) == ["p_flip", "Bayes", "Mis-spec. BP", "Standard TF"] and back == out
+    assert back["p_flip"] == [10, 20, 30]

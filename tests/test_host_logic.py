@@ -164,3 +164,20 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "trees/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_reference_json_writer_layout(tmp_path):
+    """write_reference_json keeps the reference's on-disk contract (figures/eval-clip-ood.py:107-109): the
+    columns p_flip / Bayes / Mis-spec. BP, extra model columns appended, indent=4; rejects ragged columns."""
+    import json
+    from ghm_b200 import sweeps
+    res = {"p_flip": [2, 4], "Bayes": [0.4, 0.41], "Bayes SE": [0.01, 0.01], "Mis-spec. BP": [0.45, 0.43]}
+    p = tmp_path / "ood.json"
+    sweeps.write_reference_json(res, p, extra={"Guided TF": [0.5, 0.6]})
+    text = p.read_text()
+    assert text.startswith('{\n    "p_flip": [\n        2,')
+    assert list(json.loads(text)) == ["p_flip", "Bayes", "Mis-spec. BP", "Guided TF"]
+    import pytest
+    with pytest.raises(ValueError):
+        sweeps.write_reference_json(res, p, extra={"bad": [1.0]})
+    assert sweeps.DEFAULT_P_GRID == tuple(range(2, 42, 2))
