@@ -357,12 +357,9 @@ static int expand_launch(const ExpandAll& a, cudaStream_t st) {
 // Levels near the root keep only the first warp(s) of a CTA busy, and warp w of every CTA lives on scheduler w % 4:
 // rotate the thread -> work-item mapping by (CTA, level) so those single-warp rounds spread over the four schedulers.
 __device__ __forceinline__ int rot_tid(int l) {
-    const int nw = blockDim.x >> 5;
-    int t = (int)threadIdx.x + 32 * (int)((blockIdx.x + (unsigned)l) % (unsigned)nw);
-    return t >= (int)blockDim.x ? t - (int)blockDim.x : t;
+    return (int)((threadIdx.x + 32u * (blockIdx.x + (unsigned)l)) & (blockDim.x - 1u));     // block size is a power of two
 }
 
-#define GF_NT 256                                            // launch bound; the block size is a launch parameter
 #define GF_NT_CLS 128                                        // measured best: 128 threads for the cls set, 256 for the dns set
 #define GF_NT_DNS 256
 struct FusedExp {
@@ -373,18 +370,21 @@ struct FusedExp {
     float* out[GHM_EXP_MAX_T];
 };
 
-#define GF_CH 8                                              // table entries a thread holds per chunk
-template <bool VEC2>
+#define GF_CH 6                                              // table entries a thread holds per chunk
+template <bool VEC2, int NT>
 __device__ __forceinline__ void expand_tab(const FusedExp& e, const float* gsm, int64_t tree0, int g) {
     typedef typename std::conditional<VEC2, float2, float>::type U;
-    const int stride = e.stride, NT = blockDim.x;
-    // work list = (tensor, chunk of GF_CH * GF_NT units).  Global loads queue behind the stores already in the
-    // memory pipe, so the offsets of the NEXT chunk are fetched before the stores of the current one are issued.
+    const char* sbase = reinterpret_cast<const char*>(gsm);
+    const unsigned tstride = (unsigned)e.stride * 4u;          // bytes per tree per array
+    // work list = (tensor, chunk of GF_CH * NT units).  Global loads queue behind the stores already in the memory
+    // pipe, so the offsets of the NEXT chunk are fetched before the stores of the current one are issued.  Within a
+    // chunk the tree is the outer loop: the GF_CH stores of a tree sit at compile-time distances (k * NT units) from
+    // one pointer, so a store costs one shared-memory address add, one LDS and one STG.
     auto fetch = [&](int ti, int base, unsigned (&o)[GF_CH]) {
         const uint16_t* __restrict__ tab = e.tab + e.tab_off[ti] + base + threadIdx.x;
         const int left = e.upt[ti] - base - (int)threadIdx.x;
 #pragma unroll
-        for (int k = 0; k < GF_CH; ++k) o[k] = (k * NT < left) ? (unsigned)__ldg(tab + k * NT) : 0u;
+        for (int k = 0; k < GF_CH; ++k) o[k] = (k * NT < left) ? (unsigned)__ldg(tab + k * NT) * 4u : 0u;
     };
     unsigned cur[GF_CH], nxt[GF_CH];
     int ti = 0, base = 0;
@@ -396,23 +396,14 @@ __device__ __forceinline__ void expand_tab(const FusedExp& e, const float* gsm, 
         if (nti < e.n_t) fetch(nti, nbase, nxt);
         U* __restrict__ out = reinterpret_cast<U*>(e.out[ti]) + tree0 * upt + base + threadIdx.x;
         const int left = upt - base - (int)threadIdx.x;
+        const char* sa = sbase;
+#pragma unroll 2
+        for (int tr = 0; tr < g; ++tr, sa += tstride, out += upt) {
 #pragma unroll
-        for (int k = 0; k < GF_CH; ++k) {
-            if (k * NT < left) {
-                const float* sp = gsm + cur[k];
-                U* o = out + k * NT;
-                int tr = 0;
-                for (; tr + 4 <= g; tr += 4) {
-                    const U v0 = *reinterpret_cast<const U*>(sp + (tr + 0) * stride);
-                    const U v1 = *reinterpret_cast<const U*>(sp + (tr + 1) * stride);
-                    const U v2 = *reinterpret_cast<const U*>(sp + (tr + 2) * stride);
-                    const U v3 = *reinterpret_cast<const U*>(sp + (tr + 3) * stride);
-                    o[(size_t)(tr + 0) * upt] = v0;
-                    o[(size_t)(tr + 1) * upt] = v1;
-                    o[(size_t)(tr + 2) * upt] = v2;
-                    o[(size_t)(tr + 3) * upt] = v3;
+            for (int k = 0; k < GF_CH; ++k) {
+                if (k * NT < left) {
+                    out[k * NT] = *reinterpret_cast<const U*>(sa + cur[k]);
                 }
-                for (; tr < g; ++tr) o[(size_t)tr * upt] = *reinterpret_cast<const U*>(sp + tr * stride);
             }
         }
 #pragma unroll
@@ -422,7 +413,7 @@ __device__ __forceinline__ void expand_tab(const FusedExp& e, const float* gsm, 
 }
 
 template <int Q, bool EX, bool VEC2>
-__global__ void __launch_bounds__(GF_NT) k_guides_dns_fused(const GhmDev d, const LvlArgs a, const __grid_constant__ FusedExp e,
+__global__ void __launch_bounds__(GF_NT_DNS) k_guides_dns_fused(const GhmDev d, const LvlArgs a, const __grid_constant__ FusedExp e,
                                                             int G) {
     extern __shared__ __align__(16) float gsm[];
     const int L = d.L;
@@ -448,7 +439,7 @@ __global__ void __launch_bounds__(GF_NT) k_guides_dns_fused(const GhmDev d, cons
         }
         __syncthreads();
     }
-    expand_tab<VEC2>(e, gsm, tree0, g);
+    expand_tab<VEC2, GF_NT_DNS>(e, gsm, tree0, g);
 }
 
 // ---- packed / constant-bank variant of the fused dns kernel (translation-invariant tables, q == Q) ----------------
@@ -488,7 +479,7 @@ __device__ __forceinline__ void f2_log_matvec_c(const float* __restrict__ T, con
 }
 
 template <int Q, bool VEC2, int NW>
-__global__ void __launch_bounds__(GF_NT)
+__global__ void __launch_bounds__(GF_NT_DNS)
 k_guides_dns_fused_c(const __grid_constant__ GhmDev d, const __grid_constant__ LvlArgs a, const __grid_constant__ FusedExp e,
                      const __grid_constant__ GuideC gc, int G, const __grid_constant__ DnsTab<NW> tab) {
     extern __shared__ __align__(16) float gsm[];
@@ -604,11 +595,11 @@ k_guides_dns_fused_c(const __grid_constant__ GhmDev d, const __grid_constant__ L
         }
         __syncthreads();
     }
-    expand_tab<VEC2>(e, gsm, tree0, g);
+    expand_tab<VEC2, GF_NT_DNS>(e, gsm, tree0, g);
 }
 
 template <int Q, bool EX, bool VEC2>
-__global__ void __launch_bounds__(GF_NT) k_guides_cls_fused(const GhmDev d, const LvlArgs a, const __grid_constant__ FusedExp e,
+__global__ void __launch_bounds__(GF_NT_CLS) k_guides_cls_fused(const GhmDev d, const LvlArgs a, const __grid_constant__ FusedExp e,
                                                             int G) {
     extern __shared__ __align__(16) float gsm[];
     const int L = d.L;
@@ -625,7 +616,7 @@ __global__ void __launch_bounds__(GF_NT) k_guides_cls_fused(const GhmDev d, cons
         }
         __syncthreads();
     }
-    expand_tab<VEC2>(e, gsm, tree0, g);
+    expand_tab<VEC2, GF_NT_CLS>(e, gsm, tree0, g);
 }
 
 // trees per CTA of the fused kernels for `arrays` compact arrays; 0 -> does not fit, use the level kernels
