@@ -619,6 +619,91 @@ __global__ void __launch_bounds__(GF_NT_CLS) k_guides_cls_fused(const GhmDev d, 
     expand_tab<VEC2, GF_NT_CLS>(e, gsm, tree0, g);
 }
 
+// ---- packed / constant-bank variant of the fused cls kernel (translation-invariant tables, q == Q) ----------------
+// Internal levels as in k_guides_dns_fused_c (uniform matrix index, tables in the constant bank).  The leaf level
+// gathers rows log T_c[:, x] (:196) of the s leaf-level matrices from a shared-memory copy: the row index depends on
+// the observed leaf, so it cannot come through the uniform path, and a global gather would queue behind the stores.
+template <int Q, bool VEC2, int NW>
+__global__ void __launch_bounds__(GF_NT_CLS)
+k_guides_cls_fused_c(const __grid_constant__ GhmDev d, const __grid_constant__ LvlArgs a, const __grid_constant__ FusedExp e,
+                     const __grid_constant__ GuideC gc, int G, const __grid_constant__ DnsTab<NW> tab) {
+    extern __shared__ __align__(16) float gsm[];
+    constexpr int H = Q / 2, QQ = Q * Q;
+    const int L = d.L, s = d.s, nL = d.n_leaves;
+    const int stride = e.stride, NT = blockDim.x, tid = threadIdx.x;
+    float* HD = gsm;
+    float* LT = gsm + (size_t)G * stride;                   // [s][Q][Q] log T^T of the edges into the leaves
+    const int64_t tree0 = (int64_t)blockIdx.x * G;
+    const int g = (int)min((int64_t)G, a.B - tree0);
+    const float* Tup = tab.v;
+    {
+        const float* src = d.TlogT + (size_t)d.mat_off[L] * QQ;
+        for (int i = tid; i < s * QQ; i += NT) LT[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    int tmb = gc.up_base - gc.s_u;                          // matrices of the edges into depth L-1
+    for (int l = L - 1; l >= 0; --l) {
+        const int n = d.spow[l], items = g * n;
+        const unsigned nm = d.pow_magic[l];
+        const int noff_c = 1 + d.edge_off[l + 1], noff_p = l == 0 ? 0 : 1 + d.edge_off[l];
+        const int rt = rot_tid(l);
+        for (int w0 = 0; w0 < items; w0 += NT) {
+            const bool act = w0 + rt < items;
+            if (!__any_sync(0xffffffffu, act)) continue;
+            const int w = act ? w0 + rt : items - 1;
+            const int t = div_magic(w, n, nm), idx = w - t * n;
+            float* hd = HD + t * stride;
+            f2 acc[H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) acc[i] = make_float2(0.f, 0.f);
+            if (l == L - 1) {
+                for (int c = 0; c < s; ++c) {
+                    const int x = leaf_at(a.leaves, a.leaf_dtype, (tree0 + t) * nL + idx * s + c, Q, d.status);
+                    f2 r[H];
+                    f2_ld<H>(LT + (c * Q + x) * Q, r);
+#pragma unroll
+                    for (int i = 0; i < H; ++i) { acc[i].x += r[i].x; acc[i].y += r[i].y; }
+                }
+            } else {
+                int tm = tmb;
+#pragma unroll 1
+                for (int c = 0; c < s; ++c, ++tm) {
+                    f2 h[H], m[H];
+                    f2_ld<H>(hd + (noff_c + idx * s + c) * Q, h);
+                    f2_log_matvec_c<Q>(Tup + tm * QQ, h, m);    // log(T @ exp(hd))  (:207)
+#pragma unroll
+                    for (int i = 0; i < H; ++i) { acc[i].x += m[i].x; acc[i].y += m[i].y; }
+                }
+            }
+            const float mx = f2_vmax<H>(acc);                   // (:197,208)
+#pragma unroll
+            for (int i = 0; i < H; ++i) { acc[i].x -= mx; acc[i].y -= mx; }
+            if (act) f2_st<H>(hd + (noff_p + idx) * Q, acc);
+            if (l == 0 && act) {
+                const int64_t b = tree0 + t;
+                if (a.root_hd) f2_st<H>(a.root_hd + b * Q, acc);
+                if (a.post) {                                   // posterior = softmax(hd + log p_y)  (:213-217)
+                    f2 h0[H];
+#pragma unroll
+                    for (int i = 0; i < H; ++i)
+                        h0[i] = make_float2(acc[i].x + logf(__ldg(d.py + 2 * i)), acc[i].y + logf(__ldg(d.py + 2 * i + 1)));
+                    const float m0 = f2_vmax<H>(h0);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int i = 0; i < H; ++i) { h0[i].x = expf(h0[i].x - m0); h0[i].y = expf(h0[i].y - m0); sum += h0[i].x + h0[i].y; }
+                    const float inv = 1.0f / sum;
+#pragma unroll
+                    for (int i = 0; i < H; ++i) { h0[i].x *= inv; h0[i].y *= inv; }
+                    f2_st<H>(a.post + b * Q, h0);
+                }
+            }
+        }
+        if (l < L - 1) tmb -= gc.s_u;
+        __syncthreads();
+    }
+    expand_tab<VEC2, GF_NT_CLS>(e, gsm, tree0, g);
+}
+
 // trees per CTA of the fused kernels for `arrays` compact arrays; 0 -> does not fit, use the level kernels
 static int fused_trees_per_cta(int64_t n_nodes, int q, int arrays) {
     const size_t per_tree = (size_t)arrays * n_nodes * q * sizeof(float);
@@ -748,6 +833,22 @@ extern "C" int ghm_guides_cls(const ghm_model_t* m, int64_t B, const void* leave
                 GHM_CHECK_LAUNCH();
                 return GHM_OK;
             };
+            const size_t words = (size_t)d.n_mat * Q * Q;
+            const size_t dyn_c = dyn + (size_t)d.s * Q * Q * sizeof(float);
+            if (d.ti && d.q == Q && 2 * words <= (size_t)GHM_TAB_WORDS && ((uintptr_t)root_hd % 8) == 0 &&
+                (!post || ((uintptr_t)post % 8) == 0)) {
+                GuideC gc{(d.L - 1) * d.s, (int)words, d.s};
+                DnsTab<GHM_TAB_WORDS> tab;
+                tab.v[0] = 0.f;
+                memcpy(tab.v, m->h_TlinT, words * sizeof(float));
+                auto goc = [&](auto kern) -> int {
+                    GHM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_c));
+                    kern<<<grid, GF_NT_CLS, dyn_c, st>>>(d, a, fe, gc, G, tab);
+                    GHM_CHECK_LAUNCH();
+                    return GHM_OK;
+                };
+                return v2 ? goc(k_guides_cls_fused_c<Q, true, GHM_TAB_WORDS>) : goc(k_guides_cls_fused_c<Q, false, GHM_TAB_WORDS>);
+            }
             if (d.q == Q) return v2 ? go(k_guides_cls_fused<Q, true, true>) : go(k_guides_cls_fused<Q, true, false>);
             return v2 ? go(k_guides_cls_fused<Q, false, true>) : go(k_guides_cls_fused<Q, false, false>);
         });
