@@ -194,7 +194,20 @@ def run_ours(args, rank, world, local_rank):
         # NCCL's 24-byte all-reduce must not be starved by the compute kernels that already fill every SM: give its
         # stream priority so its single CTA is placed as soon as one of ours retires
         opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        # stdout carries exactly one JSON line: the communicator banner ("NCCL version ...", written to fd 1 from native
+        # code) is sent to stderr by pointing fd 1 there while the communicator is created
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     u = np.ones(Q) / Q
     sampler = ClipSampler(N_LAYERS, N_CHILDS, [u, u], P_FLIPS, K=K_CLIP, variable_type=Q, device=dev, rng="philox",
                           seed=1234)
