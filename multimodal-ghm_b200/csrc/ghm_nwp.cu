@@ -18,9 +18,11 @@
 // broadcast loads, and the launch has B*(n_L-1) threads instead of B.  LINEAR domain with a max-rescale
 // wherever the reference shifts; guide tensors are the natural logs of those rescaled vectors, i.e. the
 // reference's shifted log-messages (including the aliased root halves, :425-439).
+#include <string.h>
+
 #include <algorithm>
 
-#include "ghm_vec.cuh"
+#include "ghm_vec2.cuh"
 
 #define NWP_NT 128
 #define NWP_MAX_GUIDES (2 * GHM_MAX_LEVELS + 1)
@@ -240,10 +242,267 @@ __global__ void __launch_bounds__(NWP_NT) k_nwp_pos(const GhmDev d, const NwpArg
     store_row<Q>(a.pp + row * q, bel, q);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Uniform variant (translation-invariant tables, q == Q even): one thread per TREE, the position is a property of
+// the CTA (blockIdx.y strides over the positions), so every path index -- ancestors, child numbers, matrices,
+// the depth at which the goal path splits off -- is the same for all threads: the 2L-1 matvecs of a position take
+// their table from the constant bank through uniform registers (no per-lane table rows through the LSU, which is
+// what bounds k_nwp_pos), and the finished-subtree messages live transposed, FT[node][state pair][tree], so that
+// consecutive trees read them coalesced.
+// ------------------------------------------------------------------------------------------------
+struct NwpU { int up0, dn_off, s_u, pg; };                   // (L-2)*s, float offset of Tlin in the table parameter, s, gridDim.y
+
+template <int H>
+__device__ __forceinline__ void f2_mul_into(f2 (&h)[H], const f2 (&f)[H]) {
+#pragma unroll
+    for (int i = 0; i < H; ++i) h[i] = f2_mul(h[i], f[i]);
+}
+// rescaled leaf message T_c[:, x] from the shared-memory copy of the leaf-level matrices (:374-375)
+template <int Q>
+__device__ __forceinline__ void nwp_leaf_msg_s(const float* LT, int c, int x, f2 (&m)[Q / 2]) {
+    const f2* r = reinterpret_cast<const f2*>(LT + (c * Q + x) * Q);
+#pragma unroll
+    for (int i = 0; i < Q / 2; ++i) m[i] = r[i];
+    f2_normalize<Q>(m);
+}
+
+template <int Q, int NW>
+__global__ void __launch_bounds__(NWP_NT)
+k_nwp_full_u(const __grid_constant__ GhmDev d, const __grid_constant__ NwpArgs a, const __grid_constant__ NwpU u,
+             const __grid_constant__ DnsTab<NW> tab) {
+    extern __shared__ __align__(16) float nsm[];
+    constexpr int H = Q / 2, QQ = Q * Q;
+    const int L = d.L, s = d.s, nL = d.n_leaves, tid = threadIdx.x;
+    float* LT = nsm;
+    {
+        const float* src = d.TlinT + (size_t)d.mat_off[L] * QQ;
+        for (int i = tid; i < s * QQ; i += NWP_NT) LT[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int64_t b0 = (int64_t)blockIdx.x * NWP_NT + tid;
+    const bool act = b0 < a.B;
+    const int64_t b = act ? b0 : a.B - 1;
+    f2* FT = reinterpret_cast<f2*>(a.full);
+    const int64_t B = a.B;
+    int lbase = u.up0;                                        // matrices of the edges into depth l
+    for (int l = L - 1; l >= 1; --l, lbase -= u.s_u) {
+        const int n = d.spow[l];
+        const int noff = nwp_node(d, l), noff_c = nwp_node(d, l + 1);
+        int toff = lbase;
+        for (int idx = 0; idx < n; ++idx) {
+            f2 h[H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) h[i] = make_float2(1.f, 1.f);
+            for (int cc = 0; cc < s; ++cc) {
+                f2 f[H];
+                if (l == L - 1) nwp_leaf_msg_s<Q>(LT, cc, nwp_leaf(a, d, b * nL + idx * s + cc), f);
+                else {
+                    const f2* src = FT + (int64_t)(noff_c + idx * s + cc) * H * B + b;
+#pragma unroll
+                    for (int i = 0; i < H; ++i) f[i] = src[(int64_t)i * B];
+                }
+                f2_mul_into<H>(h, f);
+            }
+            f2_normalize<Q>(h);
+            f2 v[H];
+            f2_matvec_c<Q>(tab.v + toff * QQ, h, v);
+            f2_normalize<Q>(v);
+            if (act) {
+                f2* dst = FT + (int64_t)(noff + idx) * H * B + b;
+#pragma unroll
+                for (int i = 0; i < H; ++i) dst[(int64_t)i * B] = v[i];
+            }
+            if (++toff == lbase + u.s_u) toff = lbase;
+        }
+    }
+}
+
+#define NWP_PC 4                                             // consecutive positions per chunk: 4 rows of q floats = 16q bytes,
+                                                             // whole 32-byte sectors for even q
+template <int Q, int NW>
+__global__ void __launch_bounds__(NWP_NT)
+k_nwp_pos_u(const __grid_constant__ GhmDev d, const __grid_constant__ NwpArgs a, const __grid_constant__ NwpU u,
+            const __grid_constant__ DnsTab<NW> tab) {
+    extern __shared__ __align__(16) float nsm[];
+    constexpr int H = Q / 2, QQ = Q * Q, NT = NWP_NT, PC = NWP_PC;
+    const int L = d.L, s = d.s, nL = d.n_leaves, tid = threadIdx.x;
+    const int npos = nL - 1;
+    float* LT = nsm;                                         // [s][Q][Q]
+    f2* HS = reinterpret_cast<f2*>(nsm + (size_t)((s * QQ + 3) / 4) * 4);   // [L][H][NT]  path hd (depth 1..L-1)
+    f2* QS = HS + (size_t)L * H * NT;                        // [L][H][NT]  path qd
+    f2* ST = QS + (size_t)L * H * NT;                        // [NT][PC][H] posterior rows of the chunk, flushed coalesced
+    uint8_t* LV = reinterpret_cast<uint8_t*>(ST + (size_t)NT * PC * H);     // [PC + s][NT] observed leaves of the chunk
+    {
+        const float* src = d.TlinT + (size_t)d.mat_off[L] * QQ;
+        for (int i = tid; i < s * QQ; i += NT) LT[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int64_t cta0 = (int64_t)blockIdx.x * NT;
+    const int64_t b0 = cta0 + tid;
+    const bool act = b0 < a.B;
+    const int64_t b = act ? b0 : a.B - 1;
+    const int64_t B = a.B;
+    const f2* FT = reinterpret_cast<const f2*>(a.full);
+    const float* Tup = tab.v;
+    const float* Tdn = tab.v + u.dn_off;
+    f2 ex[H];                                                // external root message, linear domain (:425-435)
+    if (a.ext) {
+        const f2* xe = reinterpret_cast<const f2*>(a.ext + b * Q);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < H; ++i) { ex[i] = xe[i]; mx = fmaxf(mx, fmaxf(ex[i].x, ex[i].y)); }
+#pragma unroll
+        for (int i = 0; i < H; ++i) ex[i] = make_float2(__expf(ex[i].x - mx), __expf(ex[i].y - mx));
+    }
+    for (int t0 = blockIdx.y * PC; t0 < npos; t0 += u.pg * PC) {     // uniform: the positions are the same for the whole CTA
+        const int nv = min(PC, npos - t0);
+        // the leaves this chunk conditions on beyond the finished subtrees: from the first sibling of leaf t0 to leaf
+        // t0+nv-1, fetched with independent loads (one memory latency per chunk instead of one per use)
+        const int lbase = ghm_div_s(t0, d) * s;
+        const int nlv = t0 + nv - lbase;
+        for (int j = 0; j < nlv; ++j) LV[j * NT + tid] = (uint8_t)nwp_leaf(a, d, b * nL + lbase + j);
+        for (int p = 0; p < nv; ++p) {
+            const int t = t0 + p;
+            f2 m[H];
+            {
+                const int pt = ghm_div_s(t, d);
+                nwp_leaf_msg_s<Q>(LT, t - pt * s, LV[(t - lbase) * NT + tid], m);
+            }
+            // ---- up the path: depth L-1 .. 1 (:389-415) ----
+            int idx = t;
+            for (int l = L - 1; l >= 1; --l) {
+                const int pidx = ghm_div_s(idx, d);
+                const int c = idx - pidx * s;
+                f2 h[H];
+#pragma unroll
+                for (int i = 0; i < H; ++i) h[i] = m[i];
+                for (int cc = 0; cc < c; ++cc) {             // finished children left of the path
+                    f2 f[H];
+                    if (l == L - 1) nwp_leaf_msg_s<Q>(LT, cc, LV[(pidx * s + cc - lbase) * NT + tid], f);
+                    else {
+                        const f2* src = FT + (int64_t)(nwp_node(d, l + 1) + pidx * s + cc) * H * B + b;
+#pragma unroll
+                        for (int i = 0; i < H; ++i) f[i] = src[(int64_t)i * B];
+                    }
+                    f2_mul_into<H>(h, f);
+                }
+                f2_normalize<Q>(h);
+                const int pc = pidx - ghm_div_s(pidx, d) * s;
+                f2_matvec_c<Q>(Tup + ((l - 1) * s + pc) * QQ, h, m);
+                f2_normalize<Q>(m);
+                f2* Hl = HS + (size_t)l * H * NT + tid;
+                f2* Ql = QS + (size_t)l * H * NT + tid;
+#pragma unroll
+                for (int i = 0; i < H; ++i) { Hl[i * NT] = h[i]; Ql[i * NT] = m[i]; }
+                idx = pidx;
+            }
+            // ---- root (:420-439): idx is the depth-1 node on the path ----
+            f2 bel[H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) bel[i] = m[i];
+            for (int cc = 0; cc < idx; ++cc) {
+                f2 f[H];
+                const f2* src = FT + (int64_t)(nwp_node(d, 1) + cc) * H * B + b;
+#pragma unroll
+                for (int i = 0; i < H; ++i) f[i] = src[(int64_t)i * B];
+                f2_mul_into<H>(bel, f);
+            }
+            f2_normalize<Q>(bel);
+            if (a.ext) { f2_mul_into<H>(bel, ex); f2_normalize<Q>(bel); }
+            // ---- down the path of leaf t+1 (:443-459) ----
+            for (int l = 1; l <= L; ++l) {
+                const int gl = ghm_div_pow(t + 1, L - l, d);  // goal-path node at depth l
+                const int al = ghm_div_pow(t, L - l, d);      // observed-path node at depth l
+                const int cg = gl - ghm_div_s(gl, d) * s;
+                const float* Tm = Tdn + ((l - 1) * s + cg) * QQ;
+                f2 tt[H];
+                if (gl == al) {                               // shared ancestor: cavity update (l <= L-1 here)
+                    const f2* Hl = HS + (size_t)l * H * NT + tid;
+                    const f2* Ql = QS + (size_t)l * H * NT + tid;
+                    f2 w[H];
+#pragma unroll
+                    for (int i = 0; i < H; ++i) {
+                        const f2 qv = Ql[i * NT];
+                        w[i].x = qv.x > 0.f ? __fdividef(bel[i].x, qv.x) : 0.f;
+                        w[i].y = qv.y > 0.f ? __fdividef(bel[i].y, qv.y) : 0.f;
+                    }
+                    f2_matvec_c<Q>(Tm, w, tt);
+#pragma unroll
+                    for (int i = 0; i < H; ++i) bel[i] = f2_mul(Hl[i * NT], tt[i]);
+                } else {
+                    f2_matvec_c<Q>(Tm, bel, tt);
+#pragma unroll
+                    for (int i = 0; i < H; ++i) bel[i] = tt[i];
+                }
+                f2_normalize<Q>(bel);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < H; ++i) sum += bel[i].x + bel[i].y;
+            const float inv = 1.0f / sum;
+            f2* srow = ST + ((size_t)tid * PC + p) * H;
+#pragma unroll
+            for (int i = 0; i < H; ++i) srow[i] = make_float2(bel[i].x * inv, bel[i].y * inv);
+        }
+        __syncthreads();
+        // flush: the nv rows of a tree are nv*q contiguous floats of pp; consecutive lanes write consecutive 8-byte units
+        const int upt = nv * H;
+        const int ntree = (int)min((int64_t)NT, B - cta0);
+        if (nv == PC) {                                       // compile-time divisor on the common path
+            for (int v = tid; v < ntree * (PC * H); v += NT) {
+                const int tr = v / (PC * H), k = v - tr * (PC * H);
+                reinterpret_cast<f2*>(a.pp + ((cta0 + tr) * npos + t0) * Q)[k] = ST[(size_t)tr * PC * H + k];
+            }
+        } else {
+            for (int v = tid; v < ntree * upt; v += NT) {
+                const int tr = v / upt, k = v - tr * upt;
+                reinterpret_cast<f2*>(a.pp + ((cta0 + tr) * npos + t0) * Q)[k] = ST[(size_t)tr * PC * H + k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// GHM_EUNSUP -> the caller takes the generic kernels
+template <int Q, bool GUIDE>
+static int launch_nwp_u(const ghm_model* m, const NwpArgs& a, cudaStream_t st) {
+    const GhmDev& d = m->d;
+    constexpr int NW = GHM_TAB_WORDS;
+    const size_t words = (size_t)d.n_mat * Q * Q;
+    if (!d.ti || d.q != Q || d.s < 2 || d.s > 16 || d.L < 2 || 2 * words > (size_t)NW) return GHM_EUNSUP;
+    if (((uintptr_t)a.pp % 8) || ((uintptr_t)a.full % 8) || (a.ext && ((uintptr_t)a.ext % 8))) return GHM_EUNSUP;
+    if (GUIDE) return GHM_EUNSUP;                             // guide rows of one position sit 4q(n_L-1) bytes apart between
+                                                             // trees: the (tree, position)-per-thread kernel writes them better
+    const size_t lt = ((size_t)d.s * Q * Q + 3) / 4 * 4 * sizeof(float);
+    const size_t dyn_pos = lt + ((size_t)2 * d.L + NWP_PC) * (Q / 2) * NWP_NT * sizeof(float2) + (size_t)(NWP_PC + d.s) * NWP_NT;
+    if (dyn_pos > 100 * 1024) return GHM_EUNSUP;
+    const int npos = d.n_leaves - 1;
+    const unsigned gx = (unsigned)((a.B + NWP_NT - 1) / NWP_NT);
+    // enough position groups to fill the GPU a few times over
+    const int nchunk = (npos + NWP_PC - 1) / NWP_PC;
+    int pg = (int)std::min<int64_t>(nchunk, std::max<int64_t>(1, (148 * 16 + gx - 1) / gx));
+    if (pg > 65535) pg = 65535;
+    NwpU u{(d.L - 2) * d.s, (int)words, d.s, pg};
+    DnsTab<NW> tab;
+    tab.v[0] = 0.f;
+    memcpy(tab.v, m->h_TlinT, words * sizeof(float));
+    memcpy(tab.v + words, m->h_Tlin, words * sizeof(float));
+    k_nwp_full_u<Q, NW><<<gx, NWP_NT, lt, st>>>(d, a, u, tab);
+    GHM_CHECK_LAUNCH();
+    GHM_CUDA_TRY(cudaFuncSetAttribute(k_nwp_pos_u<Q, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_pos));
+    k_nwp_pos_u<Q, NW><<<dim3(gx, (unsigned)pg), NWP_NT, dyn_pos, st>>>(d, a, u, tab);
+    GHM_CHECK_LAUNCH();
+    return GHM_OK;
+}
+
 // ----------------------------------------------------------------------------------------
 template <int Q, bool GUIDE>
 static int launch_nwp(const ghm_model* m, const NwpArgs& a, cudaStream_t st) {
     const GhmDev& d = m->d;
+    {
+        const int rc = launch_nwp_u<Q, GUIDE>(m, a, st);
+        if (rc != GHM_EUNSUP) return rc;
+    }
     for (int l = d.L - 1; l >= 1; --l) {
         const int64_t nthreads = a.B * d.spow[l];
         k_nwp_full<Q><<<(unsigned)((nthreads + NWP_NT - 1) / NWP_NT), NWP_NT, 0, st>>>(d, a, l);
