@@ -27,7 +27,7 @@ from . import ops
 from . import data_random_GHM as G
 from .sharding import mean_se_from_sums
 
-__all__ = ["clip_ood_sweep", "vlm_ood_sweep", "cdm_ood_sweep", "write_reference_json", "DEFAULT_P_GRID"]
+__all__ = ["clip_ood_sweep", "vlm_ood_sweep", "cdm_ood_sweep", "cdm_sigma_sweep", "write_reference_json", "DEFAULT_P_GRID"]
 
 DEFAULT_P_GRID = tuple(int(p) for p in np.arange(2, 42, 2))          # percent, as the reference stores it
 
@@ -147,6 +147,35 @@ def cdm_ood_sweep(p_list=None, p_model=0.2, sigma=1.0, n_eval=10000, batch_size=
         mean = ref.i_model.bp_dns(z, float(sigma), t_hd)
         ops.risk_cdm(mean, image_tree._leaves, sums=sums[k, 1])
     return _finish(p_list, sums)
+
+
+def cdm_sigma_sweep(sigmas=(0.1, 0.25, 0.5, 1.0, 2.0, 4.0), p_flip=0.2, n_eval=65536, n_layers=(4, 4), n_childs=(3, 3),
+                    variable_type=10, seed=1234, device=None):
+    """Bayes denoising risk across diffusion noise levels (BASELINE config 3): ONE paired sample and ONE text BP_CLS
+    give the external root message; per sigma: z = x + sigma * N(0, 1) (Philox normal), image BP_DNS conditioned on the
+    text, risk sum_leaf (m - x)^2 (reference ConditionalDenoiseSampler.get_Bayes :886-894 at that sigma).  Everything
+    stays on the device; the [n_sigma, 3] accumulator is copied back once.  Philox mode only (the reference has no
+    sigma loop whose NumPy stream could be mirrored)."""
+    q = variable_type
+    py = [_uniform(q), _uniform(q)]
+    sampler = G.ConditionalDenoiseSampler(list(n_layers), list(n_childs), py, [p_flip, p_flip], sigma=1.0, variable_type=q,
+                                          device=device, rng="philox", seed=seed)
+    _, text_tree, image_tree = sampler._paired_trees(n_eval)
+    off = sampler.tree_offset - n_eval
+    _, t_hd = sampler.t_model.bp_cls(text_tree._leaves)
+    sums = torch.zeros((len(sigmas), 3), dtype=torch.float64, device=sampler.device)
+    for k, sg in enumerate(sigmas):
+        z = sampler.i_model.gauss_noise(image_tree._leaves, float(sg), seed=(seed ^ ops.IMAGE_SEED_XOR) + 7919 * (k + 1),
+                                        tree_offset=off)
+        mean = sampler.i_model.bp_dns(z, float(sg), t_hd)
+        ops.risk_cdm(mean, image_tree._leaves, sums=sums[k])
+    host = sums.cpu()
+    res = {"sigma": [float(x) for x in sigmas], "Bayes": [], "Bayes SE": []}
+    for k in range(len(sigmas)):
+        m, se = mean_se_from_sums(host[k])
+        res["Bayes"].append(float(m))
+        res["Bayes SE"].append(float(se))
+    return res
 
 
 def write_reference_json(res, path, extra=None):

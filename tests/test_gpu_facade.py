@@ -284,3 +284,15 @@ def test_ood_sweeps_philox_consistency(tmp_path):
     back = json.load(open(tmp_path / "clip-ood.json"))
     assert list(back) == ["p_flip", "Bayes", "Mis-spec. BP", "Standard TF"] and back == out
     assert back["p_flip"] == [10, 20, 30]
+
+
+def test_cdm_sigma_sweep(G):
+    """BASELINE config 3: Bayes denoising risk over a sigma grid from one paired sample; monotone in sigma, and the
+    sigma = 1 point agrees with ConditionalDenoiseSampler.get_Bayes (independent draw) within sampling error."""
+    from ghm_b200 import sweeps
+    res = sweeps.cdm_sigma_sweep(sigmas=(0.1, 0.5, 1.0, 2.0, 4.0), n_eval=20000, seed=21)
+    b = res["Bayes"]
+    assert all(b[i] < b[i + 1] for i in range(len(b) - 1)) and b[0] > 0
+    s = G.ConditionalDenoiseSampler([4, 4], [3, 3], [u10, u10], [.2, .2], sigma=1.0, rng="philox", seed=77)
+    ref, se = s.get_Bayes(n_eval=20000)
+    assert abs(b[2] - ref) < 6 * (se + res["Bayes SE"][2])
