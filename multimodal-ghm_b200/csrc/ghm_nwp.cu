@@ -317,8 +317,9 @@ k_nwp_full_u(const __grid_constant__ GhmDev d, const __grid_constant__ NwpArgs a
     }
 }
 
-#define NWP_PC 4                                             // consecutive positions per chunk: 4 rows of q floats = 16q bytes,
-                                                             // whole 32-byte sectors for even q
+#define NWP_PC 2                                             // consecutive positions per chunk (their posterior rows are flushed as
+                                                             // one 8q-byte span per tree; 4 measured the same at B = 65536 and
+                                                             // slower at B = 10000: fewer chunks, fewer resident CTAs)
 template <int Q, int NW>
 __global__ void __launch_bounds__(NWP_NT)
 k_nwp_pos_u(const __grid_constant__ GhmDev d, const __grid_constant__ NwpArgs a, const __grid_constant__ NwpU u,
@@ -328,9 +329,9 @@ k_nwp_pos_u(const __grid_constant__ GhmDev d, const __grid_constant__ NwpArgs a,
     const int L = d.L, s = d.s, nL = d.n_leaves, tid = threadIdx.x;
     const int npos = nL - 1;
     float* LT = nsm;                                         // [s][Q][Q]
-    f2* HS = reinterpret_cast<f2*>(nsm + (size_t)((s * QQ + 3) / 4) * 4);   // [L][H][NT]  path hd (depth 1..L-1)
-    f2* QS = HS + (size_t)L * H * NT;                        // [L][H][NT]  path qd
-    f2* ST = QS + (size_t)L * H * NT;                        // [NT][PC][H] posterior rows of the chunk, flushed coalesced
+    f2* HS = reinterpret_cast<f2*>(nsm + (size_t)((s * QQ + 3) / 4) * 4);   // [L-1][H][NT]  path hd of depth 1..L-1
+    f2* QS = HS + (size_t)(L - 1) * H * NT;                  // [L-1][H][NT]  path qd
+    f2* ST = QS + (size_t)(L - 1) * H * NT;                        // [NT][PC][H] posterior rows of the chunk, flushed coalesced
     uint8_t* LV = reinterpret_cast<uint8_t*>(ST + (size_t)NT * PC * H);     // [PC + s][NT] observed leaves of the chunk
     {
         const float* src = d.TlinT + (size_t)d.mat_off[L] * QQ;
@@ -390,8 +391,8 @@ k_nwp_pos_u(const __grid_constant__ GhmDev d, const __grid_constant__ NwpArgs a,
                 const int pc = pidx - ghm_div_s(pidx, d) * s;
                 f2_matvec_c<Q>(Tup + ((l - 1) * s + pc) * QQ, h, m);
                 f2_normalize<Q>(m);
-                f2* Hl = HS + (size_t)l * H * NT + tid;
-                f2* Ql = QS + (size_t)l * H * NT + tid;
+                f2* Hl = HS + (size_t)(l - 1) * H * NT + tid;
+                f2* Ql = QS + (size_t)(l - 1) * H * NT + tid;
 #pragma unroll
                 for (int i = 0; i < H; ++i) { Hl[i * NT] = h[i]; Ql[i * NT] = m[i]; }
                 idx = pidx;
@@ -417,8 +418,8 @@ k_nwp_pos_u(const __grid_constant__ GhmDev d, const __grid_constant__ NwpArgs a,
                 const float* Tm = Tdn + ((l - 1) * s + cg) * QQ;
                 f2 tt[H];
                 if (gl == al) {                               // shared ancestor: cavity update (l <= L-1 here)
-                    const f2* Hl = HS + (size_t)l * H * NT + tid;
-                    const f2* Ql = QS + (size_t)l * H * NT + tid;
+                    const f2* Hl = HS + (size_t)(l - 1) * H * NT + tid;
+                    const f2* Ql = QS + (size_t)(l - 1) * H * NT + tid;
                     f2 w[H];
 #pragma unroll
                     for (int i = 0; i < H; ++i) {
@@ -474,7 +475,7 @@ static int launch_nwp_u(const ghm_model* m, const NwpArgs& a, cudaStream_t st) {
     if (GUIDE) return GHM_EUNSUP;                             // guide rows of one position sit 4q(n_L-1) bytes apart between
                                                              // trees: the (tree, position)-per-thread kernel writes them better
     const size_t lt = ((size_t)d.s * Q * Q + 3) / 4 * 4 * sizeof(float);
-    const size_t dyn_pos = lt + ((size_t)2 * d.L + NWP_PC) * (Q / 2) * NWP_NT * sizeof(float2) + (size_t)(NWP_PC + d.s) * NWP_NT;
+    const size_t dyn_pos = lt + ((size_t)2 * (d.L - 1) + NWP_PC) * (Q / 2) * NWP_NT * sizeof(float2) + (size_t)(NWP_PC + d.s) * NWP_NT;
     if (dyn_pos > 100 * 1024) return GHM_EUNSUP;
     const int npos = d.n_leaves - 1;
     const unsigned gx = (unsigned)((a.B + NWP_NT - 1) / NWP_NT);
