@@ -4,6 +4,7 @@ Every function allocates its outputs with ``torch.empty`` on the model's device,
 ``data_ptr()``s and ``torch.cuda.current_stream().cuda_stream`` and returns torch tensors.
 Nothing here computes on the CPU: without the CUDA library or a GPU these raise.
 """
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -20,7 +21,20 @@ def _ptr(t):
 
 
 def _stream():
+    """Raw handle of torch's current stream on the current device (the private fast path costs ~1 us; the public
+    ``torch.cuda.current_stream().cuda_stream`` builds a Stream object per call and showed up in the e2e profile)."""
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return C.c_void_p(raw(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_NULL_CTX = contextlib.nullcontext()
+
+
+def _on(device):
+    """Device guard that is a no-op when ``device`` is already current (the usual case: one process per GPU)."""
+    return _NULL_CTX if torch.cuda.current_device() == device.index else torch.cuda.device(device)
 
 
 def _leaf_code(t):
@@ -83,7 +97,7 @@ class GhmModel:
         assert len(transition) == self.L and is_translation_invariant(transition, self.s) == self.ti
         T = self._pack(transition)
         py = None if p_y is None else np.ascontiguousarray(np.asarray(p_y, dtype=np.float64))
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             check(self._lib.ghm_model_update(self._h, T.ctypes.data_as(C.c_void_p),
                                              py.ctypes.data_as(C.c_void_p) if py is not None else C.c_void_p(0),
                                              _stream()))
@@ -109,7 +123,7 @@ class GhmModel:
 
     def status(self):
         out = C.c_int(0)
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             check(self._lib.ghm_model_status(self._h, _stream(), C.byref(out)))
         return out.value
 
@@ -123,7 +137,7 @@ class GhmModel:
         """
         B = int(batch)
         dev = self.device
-        with torch.cuda.device(dev):
+        with _on(dev):
             if root is not None:
                 root = torch.as_tensor(root).to(device=dev, dtype=torch.int64).contiguous()
                 assert root.numel() == B
@@ -148,7 +162,7 @@ class GhmModel:
         leaves = leaves.contiguous()
         B = leaves.shape[0]
         assert leaves.shape[1] == self.n_leaves and leaves.device == self.device
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             post = torch.empty((B, self.q), dtype=torch.float32, device=self.device)
             hd = torch.empty((B, self.q), dtype=torch.float32, device=self.device)
             nws = self._lib.ghm_bp_cls_workspace_bytes(self._h, B)
@@ -172,7 +186,7 @@ class GhmModel:
         if ext is not None:
             ext = ext.contiguous()
             assert ext.dtype == torch.float32 and tuple(ext.shape) == (B, self.q)
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             mean = torch.empty((B, self.n_leaves), dtype=torch.float32, device=self.device)
             ws = self._workspace(self._lib.ghm_bp_dns_workspace_bytes(self._h, B))
             check(self._lib.ghm_bp_dns(self._h, B, _ptr(z), float(sigma), _ptr(ext), _ptr(mean), _ptr(ws), _stream()))
@@ -187,7 +201,7 @@ class GhmModel:
         if ext is not None:
             ext = ext.contiguous()
             assert ext.dtype == torch.float32 and tuple(ext.shape) == (B, self.q)
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             pp = torch.empty((B, self.n_leaves - 1, self.q), dtype=torch.float32, device=self.device)
             ws = self._workspace(self._lib.ghm_bp_nwp_workspace_bytes(self._h, B))
             check(self._lib.ghm_bp_nwp(self._h, B, _ptr(leaves), _leaf_code(leaves), _ptr(ext), _ptr(pp), _ptr(ws),
@@ -204,7 +218,7 @@ class GhmModel:
         """-> (L guide tensors f32 [B,n_L,q] (depth L-1..0), post [B,q], root_hd [B,q])  (reference :533-549)."""
         leaves = leaves.contiguous()
         B = leaves.shape[0]
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             guides = [torch.empty((B, self.n_leaves, self.q), dtype=torch.float32, device=self.device)
                       for _ in range(self.L)]
             post = torch.empty((B, self.q), dtype=torch.float32, device=self.device)
@@ -220,7 +234,7 @@ class GhmModel:
         q, nL = self.q, self.n_leaves
         if ext is not None:
             ext = ext.contiguous()
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             widths = [2 * q] * self.L + [2 * q] + [3 * q] * self.L
             guides = [torch.empty((B, nL, w), dtype=torch.float32, device=self.device) for w in widths]
             mean = torch.empty((B, nL), dtype=torch.float32, device=self.device)
@@ -236,7 +250,7 @@ class GhmModel:
         q, nL = self.q, self.n_leaves
         if ext is not None:
             ext = ext.contiguous()
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             widths = [q] + [2 * q] * self.L + [q] * self.L
             guides = [torch.empty((B, nL - 1, w), dtype=torch.float32, device=self.device) for w in widths]
             pp = torch.empty((B, nL - 1, q), dtype=torch.float32, device=self.device)
@@ -250,7 +264,7 @@ class GhmModel:
         """z = leaves + sigma*N(0,1) (Philox stream 1) -> f32 [B, n_L]."""
         leaves = leaves.contiguous()
         B = leaves.shape[0]
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             z = torch.empty((B, self.n_leaves), dtype=torch.float32, device=self.device)
             check(self._lib.ghm_gauss_noise(self._h, B, _ptr(leaves), _leaf_code(leaves), float(sigma), seed,
                                             tree_offset, _ptr(z), _stream()))
@@ -264,7 +278,7 @@ def sample_into(model, batch, root_mode, root_in, seed, tree_offset, root_out, l
     """Philox-mode ghm_sample into caller-owned device tensors (views allowed when contiguous): no allocation."""
     for t in (root_in, root_out, leaves_out, post_out, root_hd_out):
         assert t is None or t.is_contiguous()
-    with torch.cuda.device(model.device):
+    with _on(model.device):
         check(model._lib.ghm_sample(model._h, int(batch), root_mode, _ptr(root_in), C.c_void_p(0), seed, tree_offset,
                                     _ptr(root_out), _ptr(leaves_out),
                                     _leaf_code(leaves_out) if leaves_out is not None else LEAF_I64,
@@ -275,7 +289,7 @@ def sample_mixed_into(model, batch, n_given, root_in, seed, tree_offset, root_ou
     """ghm_sample_mixed: trees [0, n_given) take ``root_in``, the rest draw uniform roots (ClipSampler image layout)."""
     for t in (root_in, root_out, leaves_out, post_out, root_hd_out):
         assert t is None or t.is_contiguous()
-    with torch.cuda.device(model.device):
+    with _on(model.device):
         check(model._lib.ghm_sample_mixed(model._h, int(batch), int(n_given), _ptr(root_in), seed, tree_offset,
                                           _ptr(root_out), _ptr(leaves_out),
                                           _leaf_code(leaves_out) if leaves_out is not None else LEAF_I64,
@@ -287,7 +301,7 @@ def sample_paired_into(model, batch, n_shared, root_seed, seed, tree_offset, roo
     the rest draw their own; no dependency on the partner's launch, so the two may run on different streams."""
     for t in (root_out, leaves_out, post_out, root_hd_out):
         assert t is None or t.is_contiguous()
-    with torch.cuda.device(model.device):
+    with _on(model.device):
         check(model._lib.ghm_sample_paired(model._h, int(batch), int(n_shared), root_seed, seed, tree_offset,
                                            _ptr(root_out), _ptr(leaves_out),
                                            _leaf_code(leaves_out) if leaves_out is not None else LEAF_I64,
@@ -306,7 +320,7 @@ def risk_clip(t_pp, i_pp, n, K, q, sums=None, pair_lo=0, pair_hi=None):
     assert t_pp.dtype == torch.float32 and i_pp.dtype == torch.float32
     assert tuple(t_pp.shape) == (n * (K + 1), q) and tuple(i_pp.shape) == (n * (K + 1), q)
     pair_hi = n if pair_hi is None else pair_hi
-    with torch.cuda.device(t_pp.device):
+    with _on(t_pp.device):
         if sums is None:
             sums = new_sums(t_pp.device)
         check(lib.ghm_risk_clip(_ptr(t_pp), _ptr(i_pp), n, K, q, pair_lo, pair_hi, _ptr(sums), _stream()))
@@ -318,7 +332,7 @@ def risk_cdm(mean, leaves, sums=None):
     lib = get_lib()
     mean, leaves = mean.contiguous(), leaves.contiguous()
     assert mean.dtype == torch.float32 and mean.shape == leaves.shape
-    with torch.cuda.device(mean.device):
+    with _on(mean.device):
         if sums is None:
             sums = new_sums(mean.device)
         check(lib.ghm_risk_cdm(_ptr(mean), _ptr(leaves), _leaf_code(leaves), mean.shape[0], mean.shape[1],
@@ -332,7 +346,7 @@ def risk_ce(pp, target, sums=None, target_stride=1, target_offset=0, row_group=1
     pp, target = pp.contiguous(), target.contiguous()
     q = pp.shape[-1]
     rows = pp.numel() // q
-    with torch.cuda.device(pp.device):
+    with _on(pp.device):
         if sums is None:
             sums = new_sums(pp.device)
         check(lib.ghm_risk_ce(_ptr(pp), _ptr(target), _leaf_code(target), rows, q, target_stride, target_offset,
@@ -344,7 +358,7 @@ def risk_zsc(text_model, i_pp, t_leaves, sums=None):
     """Accumulate the zero-shot CE: image root posterior pushed down the text tree's leftmost path vs the first text leaf."""
     i_pp, t_leaves = i_pp.contiguous(), t_leaves.contiguous()
     assert i_pp.dtype == torch.float32 and i_pp.shape[0] == t_leaves.shape[0]
-    with torch.cuda.device(i_pp.device):
+    with _on(i_pp.device):
         if sums is None:
             sums = new_sums(i_pp.device)
         check(text_model._lib.ghm_risk_zsc(text_model._h, i_pp.shape[0], _ptr(i_pp), _ptr(t_leaves), _leaf_code(t_leaves),
