@@ -332,7 +332,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel (fused sampler + BP), from the per-launch events ------
     # k_tree2 launches of the two modalities and of consecutive steps overlap on four streams, so a per-launch event
     # interval would count its neighbours: the dominant kernel's throughput is taken over the whole timed region
-    # (all 2K launches; k_tree2 is 95 % of the GPU time in the serialised ncu launch list, profiles/r01m_launches_*).
+    # (all 2K launches; k_tree2 is 95 % of the GPU time in the serialised ncu launch list, profiles/r01p_launches_bench_clip.csv).
     launch_bytes = args.steps * (B * (8 * nLt + 4 * Q + 8) + B * (8 * nLi + 4 * Q))
     peak, peak_kind = read_peaks()
     achieved = launch_bytes / (ms * 1e-3) / 1e9
