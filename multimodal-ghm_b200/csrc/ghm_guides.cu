@@ -707,7 +707,7 @@ k_guides_cls_fused_c(const __grid_constant__ GhmDev d, const __grid_constant__ L
 // trees per CTA of the fused kernels for `arrays` compact arrays; 0 -> does not fit, use the level kernels
 static int fused_trees_per_cta(int64_t n_nodes, int q, int arrays) {
     const size_t per_tree = (size_t)arrays * n_nodes * q * sizeof(float);
-    const size_t budget = 70 * 1024;                        // 3 CTAs per SM
+    const size_t budget = 73 * 1024;                        // 3 CTAs per SM (227 KB: 3 x (73 + 1 KB reserved))
     int G = (int)(budget / per_tree);
     return G > 16 ? 16 : G;
 }
