@@ -1,3 +1,8 @@
+"""Host-side profile of the bench's end-to-end step (development aid): times `reparameterize(p_k)` + `get_Bayes(n_eval)`
+through the facade, each half separately, and prints the cProfile top entries of 200 steps.
+
+    python tools/e2e_prof.py          # needs a GPU
+"""
 import sys, time, cProfile, pstats, io
 sys.path.insert(0, "multimodal-ghm_b200")
 import numpy as np, torch
