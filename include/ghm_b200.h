@@ -129,10 +129,12 @@ GHM_API int ghm_bp_cls(const ghm_model_t* m, int64_t B, const void* leaves, int 
 /* ---- K3: Gaussian denoiser  (GHMTree.BP_DNS, :467-523) -------------------------
  *   z : f32 [B, n_L]; ext : f32 [B, q] external root log-message or NULL;
  *   mean : f32 [B, n_L] posterior mean of every leaf (posterior_mean_DNS^T)
+ *   root_bu : f32 [B, q] or NULL -- root_node.hd_message after BP_DNS: the max-shifted root hd plus ext, NOT re-shifted
+ *          (the reference's root bu_message aliases hd_message, :501-506)
  *   workspace : device scratch of ghm_bp_dns_workspace_bytes(m, B) bytes */
 GHM_API int64_t ghm_bp_dns_workspace_bytes(const ghm_model_t* m, int64_t B);
 GHM_API int ghm_bp_dns(const ghm_model_t* m, int64_t B, const float* z, float sigma, const float* ext,
-               float* mean, void* workspace, void* stream);
+               float* mean, float* root_bu, void* workspace, void* stream);
 
 /* ---- K4: next-token posterior  (GHMTree.BP_NWP_autoregressive, :336-463) -------
  *   pp : f32 [B, n_L-1, q],  pp[b,t,:] = p(leaf_{t+1} | leaves_{<=t}, ext) */

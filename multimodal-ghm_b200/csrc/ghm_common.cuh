@@ -72,13 +72,31 @@ struct ghm_model {
     float* h_TTp;        // -> TTp inside h_slab (source of the constant-bank kernel parameter)
     float* h_Tlin;       // -> Tlin / TlinT inside h_slab (constant-bank parameter of k_dns2)
     float* h_TlinT;
-    cudaEvent_t upload_done;
+    cudaEvent_t upload_done;   // fences the last H2D table upload ONLY (ghm_model_update waits on it before rewriting h_slab)
+    cudaEvent_t order_ev;      // plain stream-ordering event of the ghm_host_* entry points
     void* slab;          // single device allocation holding every table
     size_t slab_bytes;
     cudaStream_t stream; // internal stream for ghm_host_* entry points
     // host scratch for ghm_host_* (lazily sized)
     void* h_scratch; size_t h_scratch_bytes;
     void* d_scratch; size_t d_scratch_bytes;
+};
+
+// Makes `dev` (or the device that owns `ptr`) current for the lifetime of the guard: every C-ABI entry point launches
+// on the device of its model / buffers regardless of the caller's current device.
+struct GhmDeviceGuard {
+    int prev = -1;
+    explicit GhmDeviceGuard(int dev) { enter(dev); }
+    explicit GhmDeviceGuard(const void* ptr) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice) enter(at.device);
+        else cudaGetLastError();
+    }
+    ~GhmDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    GhmDeviceGuard(const GhmDeviceGuard&) = delete;
+    GhmDeviceGuard& operator=(const GhmDeviceGuard&) = delete;
+private:
+    void enter(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
 };
 
 int ghm_guides_init(ghm_model* m);        // ghm_guides.cu: builds guide_tab (current device = m->device)

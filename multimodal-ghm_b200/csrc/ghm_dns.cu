@@ -123,6 +123,11 @@ __global__ void __launch_bounds__(DNS_NT) k_dns(const GhmDev d, const DnsArgs a)
         }
     }
     // =============================== root belief ===============================================
+    if (a.root_bu && active) {                                     // log of the max-rescaled root message (+ ext, unshifted)
+#pragma unroll
+        for (int k = 0; k < Q; ++k)
+            if (k < q) a.root_bu[b * q + k] = __logf(msg[k]) + (a.ext ? a.ext[b * q + k] : 0.f);
+    }
     if (a.ext) {
         float x[Q];
 #pragma unroll
@@ -281,7 +286,7 @@ static int launch_dns2_any(const ghm_model* m, const DnsArgs& a, cudaStream_t st
 }
 
 extern "C" int ghm_bp_dns(const ghm_model_t* m, int64_t B, const float* z, float sigma, const float* ext, float* mean,
-                          void* workspace, void* stream) {
+                          float* root_bu, void* workspace, void* stream) {
     if (!m || !z || !mean || !workspace) return ghm_fail(GHM_EINVAL, "ghm_bp_dns: null argument");
     if (B <= 0) return B == 0 ? GHM_OK : ghm_fail(GHM_EINVAL, "ghm_bp_dns: negative batch");
     if (!(sigma > 0.f)) return ghm_fail(GHM_EINVAL, "ghm_bp_dns: sigma must be positive");
@@ -290,10 +295,10 @@ extern "C" int ghm_bp_dns(const ghm_model_t* m, int64_t B, const float* z, float
     if (prev != m->device) cudaSetDevice(m->device);
     DnsArgs a{};
     a.B = B; a.z = z; a.c2 = -0.5f * 1.4426950408889634f / (sigma * sigma); a.ext = ext; a.mean = mean;
-    a.scratch = (float*)workspace;
+    a.scratch = (float*)workspace; a.root_bu = root_bu;
     int rc;
     if (m->d.QW) {
-        rc = ghm_wide_bp_dns(m, B, z, sigma, ext, mean, workspace, (cudaStream_t)stream);
+        rc = ghm_wide_bp_dns(m, B, z, sigma, ext, mean, root_bu, workspace, (cudaStream_t)stream);
         if (prev != m->device) cudaSetDevice(prev);
         return rc;
     }

@@ -11,6 +11,7 @@ struct DnsArgs {
     const float* ext;      // [B, q] log-message or null
     float* mean;           // [B, n_L]
     float* scratch;        // [E_int][Q][B]
+    float* root_bu;        // [B, q] or null: root_node.hd_message after BP_DNS = shifted root hd + ext (:501-506, aliasing)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {

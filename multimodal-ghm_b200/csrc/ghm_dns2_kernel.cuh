@@ -161,6 +161,11 @@ k_dns2(const __grid_constant__ GhmDev d, const __grid_constant__ Dns2Args aa, co
         advance();
     }
     // =============================== root belief ===============================================
+    if (a.root_bu && active) {                                     // log of the max-rescaled root message (+ ext, unshifted)
+#pragma unroll
+        for (int k = 0; k < Q; ++k)
+            if (k < q) a.root_bu[b * q + k] = __logf(f2_elem<Q>(msg, k)) + (a.ext ? a.ext[b * q + k] : 0.f);
+    }
     if (a.ext) {
         float x[Q];
 #pragma unroll

@@ -529,10 +529,22 @@ k_guides_dns_fused_c(const __grid_constant__ GhmDev d, const __grid_constant__ L
                 } else {
                     f2_ld<H>(hd + (noff_c + ci) * Q, h);
                 }
-                f2_log_matvec_c<Q>(Tup + tm * QQ, h, m);        // qd = log(T @ exp(hd)) (:487,497)
-                if (act) f2_st<H>(qd + (noff_c + ci) * Q, m);
+                // qd = log(T @ exp(hd)) (:487,497) = mh + r with mh = max hd.  The parent sums the SHIFTED parts r: the
+                // omitted sum of the mh is constant over the states and cancels in the max-shift below, while leaf hd is
+                // unshifted in the reference (:485) and reaches -600 .. -4400 at small sigma, where adding mh first
+                // would round r to the float32 grid of |mh| (6e-5 at 600) before the cancellation
+                const float mh = f2_vmax<H>(h);
+                f2 ex[H], u[H];
 #pragma unroll
-                for (int i = 0; i < H; ++i) { acc[i].x += m[i].x; acc[i].y += m[i].y; }
+                for (int i = 0; i < H; ++i) ex[i] = make_float2(__expf(h[i].x - mh), __expf(h[i].y - mh));
+                f2_matvec_c<Q>(Tup + tm * QQ, ex, u);
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    const float ra = __logf(u[i].x), rb = __logf(u[i].y);
+                    m[i] = make_float2(ra + mh, rb + mh);
+                    acc[i].x += ra; acc[i].y += rb;
+                }
+                if (act) f2_st<H>(qd + (noff_c + ci) * Q, m);
             }
             const float mx = f2_vmax<H>(acc);                   // hd = sum qd(children) - max (:494-496)
 #pragma unroll
@@ -887,12 +899,15 @@ extern "C" int ghm_guides_cls(const ghm_model_t* m, int64_t B, const void* leave
 // ---- dns guides ------------------------------------------------------------------------------------
 extern "C" int64_t ghm_guides_dns_workspace_bytes(const ghm_model_t* m, int64_t B) {
     if (!m || B <= 0) return 0;
+    // tree-tiled fused kernel (messages in shared memory): no workspace; it needs non-null, 8-byte aligned guide
+    // pointers -- ghm_guides_dns fails with GHM_EINVAL if they are not and no workspace was supplied
+    if (m->gt_dns.G >= 1 && m->guide_tab) return 0;
     return 3 * B * n_nodes_all(m->d) * m->d.q * (int64_t)sizeof(float);
 }
 
 extern "C" int ghm_guides_dns(const ghm_model_t* m, int64_t B, const float* z, float sigma, const float* ext,
                               float* const* guides, float* mean, void* workspace, void* stream) {
-    if (!m || !z || !workspace) return ghm_fail(GHM_EINVAL, "ghm_guides_dns: null argument");
+    if (!m || !z) return ghm_fail(GHM_EINVAL, "ghm_guides_dns: null argument");
     if (B <= 0) return GHM_OK;
     if (!(sigma > 0.f)) return ghm_fail(GHM_EINVAL, "ghm_guides_dns: sigma must be positive");
     const GhmDev& d = m->d;
@@ -938,6 +953,9 @@ extern "C" int ghm_guides_dns(const ghm_model_t* m, int64_t B, const float* z, f
             return v2 ? go(k_guides_dns_fused<Q, false, true>) : go(k_guides_dns_fused<Q, false, false>);
         });
     }
+    if (!workspace)
+        return ghm_fail(GHM_EINVAL, "ghm_guides_dns: the level-synchronous path needs a workspace of 3*B*nodes*q floats "
+                                    "(guide pointers null / not 8-byte aligned, or the tree does not fit shared memory)");
     int rc = dispatch_q(d.q, [&](auto Qc) -> int {
         constexpr int Q = decltype(Qc)::value;
         for (int l = d.L; l >= 0; --l) {

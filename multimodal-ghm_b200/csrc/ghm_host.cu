@@ -62,15 +62,19 @@ extern "C" int ghm_host_clip_bayes(const ghm_model_t* text_c, const ghm_model_t*
     // runs concurrently on the image model's stream and the two kernels fill each other's tail waves
     const uint64_t iseed = seed ^ GHM_IMAGE_SEED_XOR;
     cudaStream_t st2 = image->stream;
-    GHM_CUDA_TRY(cudaEventRecord(text->upload_done, st));              // (re-used as a plain ordering event)
-    GHM_CUDA_TRY(cudaStreamWaitEvent(st2, text->upload_done, 0));
+    // a ghm_model_update enqueued on the caller's stream may still be copying the tables: both internal streams wait
+    // for the upload fences (upload_done is only ever recorded by ghm_model_update), ordering uses order_ev
+    GHM_CUDA_TRY(cudaStreamWaitEvent(st, text->upload_done, 0));
+    GHM_CUDA_TRY(cudaStreamWaitEvent(st2, image->upload_done, 0));
+    GHM_CUDA_TRY(cudaEventRecord(text->order_ev, st));
+    GHM_CUDA_TRY(cudaStreamWaitEvent(st2, text->order_ev, 0));
     rc = ghm_sample_paired(image, B, 2 * n, seed, iseed, tree_offset, nullptr, d_il, leaf_dtype, d_ipp, nullptr, st2);
     if (rc) return rc;
     rc = ghm_sample(text, B, GHM_ROOT_UNIFORM, nullptr, nullptr, seed, tree_offset, d_root, d_tl, leaf_dtype, d_tpp,
                     nullptr, st);
     if (rc) return rc;
-    GHM_CUDA_TRY(cudaEventRecord(image->upload_done, st2));
-    GHM_CUDA_TRY(cudaStreamWaitEvent(st, image->upload_done, 0));
+    GHM_CUDA_TRY(cudaEventRecord(image->order_ev, st2));
+    GHM_CUDA_TRY(cudaStreamWaitEvent(st, image->order_ev, 0));
     rc = ghm_risk_clip(d_tpp, d_ipp, n, K, q, 0, n, d_sums, st);
     if (rc) return rc;
     GHM_CUDA_TRY(cudaMemcpyAsync(sums_host, d_sums, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -65,8 +65,29 @@ static SlabLayout slab_layout(const GhmDev& d) {
     return o;
 }
 
-// fills the host slab from the caller's float64 matrices; validates probabilities
+// read-only validation pass: nothing is written before every input is known to be a probability, so a failed
+// ghm_model_update leaves the host slab (the source of the constant-bank kernel parameters) and the device slab
+// consistent with each other
+static int validate_tables(const GhmDev& d, const double* T_host, const double* p_y_host) {
+    const int q = d.q;
+    for (size_t mi = 0; mi < (size_t)d.n_mat; ++mi)
+        for (int a = 0; a < q; ++a)
+            for (int b = 0; b < q; ++b) {
+                const double t = T_host[(mi * q + a) * (size_t)q + b];
+                if (!(t >= 0.0) || !isfinite(t))
+                    return ghm_fail(GHM_EINVAL, "transition[%zu][%d][%d]=%g is not a probability", mi, a, b, t);
+            }
+    if (p_y_host)
+        for (int a = 0; a < q; ++a)
+            if (!(p_y_host[a] >= 0.0) || !isfinite(p_y_host[a]))
+                return ghm_fail(GHM_EINVAL, "p_y[%d]=%g is not a probability", a, p_y_host[a]);
+    return GHM_OK;
+}
+
+// fills the host slab from the caller's float64 matrices (validated by validate_tables)
 static int derive_tables(const GhmDev& d, const double* T_host, const double* p_y_host, char* hs) {
+    int vrc = validate_tables(d, T_host, p_y_host);
+    if (vrc) return vrc;
     const SlabLayout o = slab_layout(d);
     const int q = d.q, QP = d.QP, QS = d.QS;
     const size_t nm = (size_t)d.n_mat, QQ = (size_t)QP * QP;
@@ -196,6 +217,7 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     MC_TRY(cudaMemcpy(m->slab, m->h_slab, o.bytes, cudaMemcpyHostToDevice));
     MC_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     MC_TRY(cudaEventCreateWithFlags(&m->upload_done, cudaEventDisableTiming));
+    MC_TRY(cudaEventCreateWithFlags(&m->order_ev, cudaEventDisableTiming));
     MC_TRY(cudaSetDevice(prev));
 #undef MC_TRY
     char* base = (char*)m->slab;
@@ -230,6 +252,8 @@ extern "C" int ghm_model_update(ghm_model_t* m, const double* T_host, const doub
     cudaGetDevice(&prev);
     if (prev != m->device) cudaSetDevice(m->device);
     struct Restore { int p, dev; ~Restore() { if (p != dev) cudaSetDevice(p); } } restore{prev, m->device};
+    int vrc = validate_tables(m->d, T_host, p_y_host);           // before anything is rewritten
+    if (vrc) return vrc;
     GHM_CUDA_TRY(cudaEventSynchronize(m->upload_done));          // the previous upload has consumed the pinned slab
     const SlabLayout o = slab_layout(m->d);
     int rc = derive_tables(m->d, T_host, p_y_host, (char*)m->h_slab);
@@ -256,6 +280,7 @@ extern "C" int ghm_model_destroy(ghm_model_t* m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamDestroy(m->stream);
     if (m->upload_done) cudaEventDestroy(m->upload_done);
+    if (m->order_ev) cudaEventDestroy(m->order_ev);
     if (m->slab) cudaFree(m->slab);
     if (m->guide_tab) cudaFree(m->guide_tab);
     if (m->h_slab) cudaFreeHost(m->h_slab);

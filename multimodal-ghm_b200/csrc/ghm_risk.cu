@@ -77,6 +77,7 @@ extern "C" int ghm_risk_clip(const float* t_pp, const float* i_pp, int64_t n, in
                         (long long)pair_lo, (long long)pair_hi);
     const int64_t cnt = pair_hi - pair_lo;
     if (cnt == 0) return GHM_OK;
+    GhmDeviceGuard guard(sums);
     k_risk_clip<<<(unsigned)((cnt + RISK_NT - 1) / RISK_NT), RISK_NT, 0, (cudaStream_t)stream>>>(t_pp, i_pp, n, K, q,
                                                                                                  pair_lo, pair_hi, sums);
     GHM_CHECK_LAUNCH();
@@ -107,6 +108,7 @@ extern "C" int ghm_risk_cdm(const float* mean, const void* leaves, int leaf_dtyp
                             void* stream) {
     if (!mean || !leaves || !sums) return ghm_fail(GHM_EINVAL, "ghm_risk_cdm: null argument");
     if (B <= 0) return GHM_OK;
+    GhmDeviceGuard guard(sums);
     const int64_t warps = B;
     unsigned grid = (unsigned)std::min<int64_t>((warps * 32 + RISK_NT - 1) / RISK_NT, 148 * 8);
     if (leaf_dtype == GHM_LEAF_I64)
@@ -140,6 +142,7 @@ extern "C" int ghm_risk_ce(const float* pp, const void* target, int leaf_dtype, 
     if (!pp || !target || !sums) return ghm_fail(GHM_EINVAL, "ghm_risk_ce: null argument");
     if (rows <= 0) return GHM_OK;
     if (row_group <= 0) return ghm_fail(GHM_EINVAL, "ghm_risk_ce: row_group must be positive");
+    GhmDeviceGuard guard(sums);
     unsigned grid = (unsigned)std::min<int64_t>((rows + RISK_NT - 1) / RISK_NT, 148 * 8);
     if (leaf_dtype == GHM_LEAF_I64)
         k_risk_ce<int64_t><<<grid, RISK_NT, 0, (cudaStream_t)stream>>>(pp, (const int64_t*)target, rows, q, t_stride,
@@ -187,6 +190,7 @@ extern "C" int ghm_risk_zsc(const ghm_model_t* text, int64_t B, const float* i_p
     if (B <= 0) return GHM_OK;
     if (leaf_dtype != GHM_LEAF_I64 && leaf_dtype != GHM_LEAF_U8) return ghm_fail(GHM_EINVAL, "bad leaf_dtype %d", leaf_dtype);
     const GhmDev& d = text->d;
+    GhmDeviceGuard guard(text->device);
     const unsigned grid = (unsigned)std::min<int64_t>((B + RISK_NT - 1) / RISK_NT, 148 * 8);
     cudaStream_t st = (cudaStream_t)stream;
 #define ZSC_GO(Q)                                                                                           \
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(RISK_NT) k_gauss_noise(const LeafT* __restrict
         for (int h = 0; h < 2; ++h) {
             const int leaf = 2 * pi + h;
             if (leaf < nL) {
-                const float u1 = ((float)(ws[2 * h] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+                const float u1 = ((float)ws[2 * h] + 0.5f) * 2.3283064365386963e-10f;      // all 32 bits: tails to 6.7 sigma
                 const float u2 = ((float)(ws[2 * h + 1] >> 8) + 0.5f) * 5.9604644775390625e-08f;
                 const float g = sqrtf(-2.0f * logf(u1)) * cosf(6.2831853071795864f * u2);
                 z[b * nL + leaf] = (float)leaves[b * nL + leaf] + sigma * g;
@@ -238,6 +242,7 @@ extern "C" int ghm_gauss_noise(const ghm_model_t* m, int64_t B, const void* leav
                                uint64_t seed, uint64_t tree_offset, float* z, void* stream) {
     if (!m || !leaves || !z) return ghm_fail(GHM_EINVAL, "ghm_gauss_noise: null argument");
     if (B <= 0) return GHM_OK;
+    GhmDeviceGuard guard(m->device);
     const int nL = m->d.n_leaves;
     const int64_t total = B * ((nL + 1) / 2);
     unsigned grid = (unsigned)std::min<int64_t>((total + RISK_NT - 1) / RISK_NT, 148 * 16);

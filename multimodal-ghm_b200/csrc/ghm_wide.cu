@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(WR_NT) k_wide_leaf_like(const GhmDev d, int64_
 // ---- BP_DNS root belief: b_0 = h_0 * exp(ext - max) / max (:501-506) ---------------------------------
 template <int NV>
 __global__ void __launch_bounds__(WR_NT) k_wide_root_belief(const GhmDev d, int64_t B, const float* __restrict__ H0,
-                                                            const float* __restrict__ ext, float* __restrict__ BU0) {
+                                                            const float* __restrict__ ext, float* __restrict__ BU0,
+                                                            float* __restrict__ root_bu) {
     const int lane = threadIdx.x & 31;
     const int QW = d.QW, q = d.q;
     const int64_t b = (int64_t)blockIdx.x * (WR_NT / 32) + (threadIdx.x >> 5);
@@ -169,6 +170,13 @@ __global__ void __launch_bounds__(WR_NT) k_wide_root_belief(const GhmDev d, int6
     float v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = H0[b * QW + lane + 32 * i];
+    if (root_bu) {                                                 // root_node.hd_message after BP_DNS: log h_0 + ext (unshifted)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int k = lane + 32 * i;
+            if (k < q) root_bu[b * q + k] = __logf(v[i]) + (ext ? ext[b * q + k] : 0.f);
+        }
+    }
     if (ext) {
         float x[NV];
 #pragma unroll
@@ -392,7 +400,7 @@ int64_t ghm_wide_dns_workspace_bytes(const ghm_model* m, int64_t B) {
     return rows * B * d.QW * (int64_t)sizeof(float) + 256;
 }
 
-int ghm_wide_bp_dns(const ghm_model* m, int64_t B, const float* z, float sigma, const float* ext, float* mean,
+int ghm_wide_bp_dns(const ghm_model* m, int64_t B, const float* z, float sigma, const float* ext, float* mean, float* root_bu,
                     void* workspace, cudaStream_t st) {
     const GhmDev& d = m->d;
     const int L = d.L, nL = d.n_leaves;
@@ -419,7 +427,7 @@ int ghm_wide_bp_dns(const ghm_model* m, int64_t B, const float* z, float sigma, 
             GHM_CHECK_LAUNCH();
             if (l >= 1 && (rc = ghm_wide_gemm(m, B, l, n, 0, Hd + off(l) * RW, Ud + off(l) * RW, st))) return rc;
         }
-        k_wide_root_belief<NV><<<row_grid(B), WR_NT, 0, st>>>(d, B, Hd, ext, BU);
+        k_wide_root_belief<NV><<<row_grid(B), WR_NT, 0, st>>>(d, B, Hd, ext, BU, root_bu);
         GHM_CHECK_LAUNCH();
         // ---- downward ----
         for (int l = 1; l <= L; ++l) {

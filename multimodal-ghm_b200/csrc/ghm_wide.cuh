@@ -6,7 +6,7 @@ int64_t ghm_wide_cls_workspace_bytes(const ghm_model* m, int64_t B);
 int ghm_wide_bp_cls(const ghm_model* m, int64_t B, const void* leaves, int leaf_dtype, float* post, float* root_hd,
                     void* workspace, cudaStream_t st);
 int64_t ghm_wide_dns_workspace_bytes(const ghm_model* m, int64_t B);
-int ghm_wide_bp_dns(const ghm_model* m, int64_t B, const float* z, float sigma, const float* ext, float* mean,
+int ghm_wide_bp_dns(const ghm_model* m, int64_t B, const float* z, float sigma, const float* ext, float* mean, float* root_bu,
                     void* workspace, cudaStream_t st);
 
 // Y[node][b][:] = X[node][b][:] @ W[mat(level, node)]  for the n_nodes nodes of `level`;

@@ -31,7 +31,7 @@ SIGNATURES = {
     "ghm_sample_paired": (c_int, [c_vp, c_i64, c_i64, c_u64, c_u64, c_u64, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "ghm_bp_cls": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "ghm_bp_dns_workspace_bytes": (c_i64, [c_vp, c_i64]),
-    "ghm_bp_dns": (c_int, [c_vp, c_i64, c_vp, c_f, c_vp, c_vp, c_vp, c_vp]),
+    "ghm_bp_dns": (c_int, [c_vp, c_i64, c_vp, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ghm_bp_nwp_workspace_bytes": (c_i64, [c_vp, c_i64]),
     "ghm_bp_nwp": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "ghm_guides_cls": (c_int, [c_vp, c_i64, c_vp, c_int, C.POINTER(c_vp), c_vp, c_vp, c_vp]),

@@ -178,6 +178,32 @@ class _LeafColumns:
         return a.astype(dtype) if dtype is not None else a
 
 
+class _RootLevel:
+    """``T_value[0]``: a one-element list holding the (B,) root array, copied from the device on first access so
+    that sampling a tree never synchronises the host (the training feed)."""
+
+    def __init__(self, tree):
+        self._tree = tree
+
+    def __len__(self):
+        return 1
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self._tree._root_np()][k]
+        if k not in (0, -1):
+            raise IndexError("list index out of range")
+        return self._tree._root_np()
+
+    def __setitem__(self, k, v):
+        if k not in (0, -1):
+            raise IndexError("list assignment index out of range")
+        self._tree._root_override = np.asarray(v)
+
+    def __iter__(self):
+        return iter([self._tree._root_np()])
+
+
 class GHMTree:
     """Sampled GHM tree + exact BP (reference :112-613), backed by device tensors.
 
@@ -204,8 +230,8 @@ class GHMTree:
         self.device = _cuda_device(device)
         self.rng, self.seed, self.tree_offset = rng, seed, tree_offset
         self._model_hint = _model
-        self._root_hd = None          # device f32 [B, q]; root_node.hd_message
-        self._root_hd_host = None     # numpy override (after BP_DNS: hd + ext, reference aliasing :504-506)
+        self._root_hd = None          # device f32 [B, q]; root_node.hd_message (BP_CLS: shifted hd; BP_DNS: hd + ext, :504-506)
+        self._root_hd_host = None     # its (q, B) float64 host copy, made on first access
         self._post = self._mean = None
         self._dns_state = None        # (z, sigma, ext) of the last BP_DNS, for guided_info
         self._cls_guides = None
@@ -248,9 +274,12 @@ class GHMTree:
         self._leaves = out["leaves"]
         self._root = out["root"]
         self._root_host = root_host
-        self.T_value = [[self._root_np()]] + [None] * (self.n_layer - 1) + [_LeafColumns(self._leaves)]
+        self._root_override = None
+        self.T_value = [_RootLevel(self)] + [None] * (self.n_layer - 1) + [_LeafColumns(self._leaves)]
 
     def _root_np(self):
+        if self._root_override is not None:
+            return self._root_override
         if self._root_host is None:
             self._root_host = self._root.cpu().numpy()
         return self._root_host
@@ -271,10 +300,16 @@ class GHMTree:
             cols = _LeafColumns(self._leaves)
             cols._host = arr
             self.T_value[-1] = cols
-        r0 = self.T_value[0][0]
-        if r0 is not self._root_host:
-            self._root_host = np.asarray(r0)
+        lvl0 = self.T_value[0]
+        r0 = None
+        if not isinstance(lvl0, _RootLevel):                 # the caller replaced the whole root level
+            r0 = np.asarray(lvl0[0])
+        elif self._root_override is not None:                # ... or assigned T_value[0][0]
+            r0 = self._root_override
+        if r0 is not None:
+            self._root_host, self._root_override = np.asarray(r0), None
             self._root = torch.from_numpy(self._root_host.astype(np.int64)).to(self.device)
+            self.T_value[0] = _RootLevel(self)
         self.Tree = None
 
     # -- BP: root posterior (reference BP_CLS, :185-221) --------------------------------------
@@ -297,7 +332,9 @@ class GHMTree:
         zz = z if isinstance(z, torch.Tensor) else torch.from_numpy(np.asarray(z))
         zd = zz.to(self.device).T.to(torch.float32).contiguous()              # [B, n_L]
         ext = self._to_dev_bq(external_hd_message)
-        self._mean = self.model.bp_dns(zd, float(sigma), ext)
+        # root_node.hd_message after BP_DNS is hd + ext (the reference's root bu aliases hd, :501-506)
+        self._mean, self._root_hd = self.model.bp_dns(zd, float(sigma), ext, want_root_bu=True)
+        self._root_hd_host = None
         self._dns_state = (zd, float(sigma), ext)
         self.posterior_mean_DNS = self._mean.T.double().cpu().numpy()
         self.dns_flag = True
@@ -358,7 +395,50 @@ class GHMTree:
 # ------------------------------------------------------------------------------------------
 # samplers (reference :617-942)
 # ------------------------------------------------------------------------------------------
+def _posterior_out(t, async_):
+    """4th element of the get_batch tuples: float64 NumPy like the reference (a blocking device -> host copy), or --
+    ``async_=True``, the training feed -- the same values as a float64 DEVICE tensor with no host synchronisation."""
+    t = t.double()
+    return t if async_ else t.cpu().numpy()
+
+
+class LazyRisk:
+    """Handle of a risk evaluation that is still running on the device (``get_Bayes(lazy=True)``).
+
+    The {sum, sum of squares, count} accumulator is copied into pinned host memory on the issuing stream and an
+    event is recorded; ``result()`` waits for that event only.  A caller that sweeps a grid (one evaluation per
+    p_flip, figures/eval-clip-ood.py:73-79) enqueues evaluation k+1 before reading evaluation k, so the GPU never
+    idles behind the host.  ``finish`` maps the three doubles to the method's return tuple."""
+
+    def __init__(self, sums, finish):
+        self._host = torch.empty(3, dtype=torch.float64).pin_memory()
+        self._host.copy_(sums, non_blocking=True)
+        self._ev = torch.cuda.Event()
+        self._ev.record(torch.cuda.current_stream(sums.device))
+        self._finish = finish
+        self._value = None
+
+    def done(self):
+        return self._ev.query()
+
+    def result(self):
+        if self._value is None:
+            self._ev.synchronize()
+            self._value = self._finish(self._host)
+        return self._value
+
+
 class _SamplerBase:
+    #: pairs / trees per internal launch of get_Bayes (bounds the device workspace; any n_eval is accepted)
+    bayes_chunk = 262144
+
+    def _chunks(self, n, per_unit_bytes=0):
+        """[(start, size)] covering n units with at most ``bayes_chunk`` units (and about 4 GiB of scratch) per piece."""
+        c = int(self.bayes_chunk)
+        if per_unit_bytes > 0:
+            c = max(1024, min(c, (4 << 30) // int(per_unit_bytes)))
+        return [(s0, min(c, n - s0)) for s0 in range(0, n, c)]
+
     def _init_backend(self, device, rng, seed):
         self.device = _cuda_device(device)
         if rng not in ("numpy", "philox"):
@@ -519,8 +599,8 @@ def _tree_from_device(sampler, which, out, batch_size):
     t.device, t.rng, t.seed, t.tree_offset = sampler.device, sampler.rng, sampler.seed, 0
     t._model_hint = mo
     t._root_hd = t._root_hd_host = t._post = t._mean = t._dns_state = t._cls_guides = None
-    t._leaves, t._root, t._root_host = out["leaves"], out["root"], None
-    t.T_value = [[t._root_np()]] + [None] * (t.n_layer - 1) + [_LeafColumns(t._leaves)]
+    t._leaves, t._root, t._root_host, t._root_override = out["leaves"], out["root"], None, None
+    t.T_value = [_RootLevel(t)] + [None] * (t.n_layer - 1) + [_LeafColumns(t._leaves)]
     t.Tree = None
     return t
 
@@ -533,19 +613,14 @@ class ClassificationSampler(SingleSampler):
         super().__init__(n_layer, n_child, p_y, p_flip, flip_scale, variable_type, translation_invariance, seedtree,
                          device=device, rng=rng, seed=seed)
 
-    def get_batch(self, batch_size=128, guide=False, device="cpu"):
+    def get_batch(self, batch_size=128, guide=False, device="cpu", async_=False):
         tree = self._tree(batch_size)
-        leaves_values = tree._leaves.to(device)
-        root_values = tree._root.to(device)
-        if guide:
-            tree.BP_CLS()
-            guided_info = tree.guided_info(device=device)
-        else:
-            guided_info = None
-        if tree.posterior_probability_CLS is None:
-            # the reference evaluates `None.T` here (:705) -> AttributeError; keep the error behaviour
+        if not guide:
+            # the reference evaluates `None.T` here (:705) -> AttributeError after sampling; keep the error behaviour
             raise AttributeError("'NoneType' object has no attribute 'T' (ClassificationSampler.get_batch needs guide=True)")
-        return leaves_values, root_values, guided_info, tree.posterior_probability_CLS.T
+        guides, post, _ = self.model.guides_cls(tree._leaves)         # BP_CLS + guided_info in one fused kernel
+        return (tree._leaves.to(device), tree._root.to(device), [g.to(device) for g in guides],
+                _posterior_out(post, async_))
 
     def get_Bayes(self, n_eval=10000):
         """Bayes CE of the root (reference :707-720): float32 loss, torch.std (unbiased) / sqrt(n)."""
@@ -567,23 +642,21 @@ class DenoiseSampler(SingleSampler):
                          device=device, rng=rng, seed=seed)
         self.sigma = sigma
 
-    def get_batch(self, batch_size=128, guide=False, device="cpu"):
+    def get_batch(self, batch_size=128, guide=False, device="cpu", async_=False):
         tree = self._tree(batch_size)
         if self.rng == "numpy":
             zs = np.random.randn(self.n_child ** self.n_layer, batch_size) * self.sigma + np.asarray(tree.leaves_values)
             zs_dev = torch.from_numpy(zs).to(self.device).T.to(torch.float32).contiguous()
         else:
             zs_dev = self.model.gauss_noise(tree._leaves, self.sigma, seed=self.seed, tree_offset=tree.tree_offset)
-            zs = zs_dev.T
-        xs = tree._leaves.to(torch.float32).to(device)
-        if guide:
-            tree.BP_DNS(zs, self.sigma)
-            guided_info = tree.guided_info()            # reference does not forward `device` here (:737)
-        else:
-            guided_info = None
-        if tree.posterior_mean_DNS is None:
+        if not guide:                                        # reference: `None.T` after sampling and noise (:742)
             raise AttributeError("'NoneType' object has no attribute 'T' (DenoiseSampler.get_batch needs guide=True)")
-        return zs_dev.to(device), xs, guided_info, tree.posterior_mean_DNS.T
+        xs = tree._leaves.to(torch.float32).to(device)
+        guides, mean = self.model.guides_dns(zs_dev, float(self.sigma), None)
+        # the reference does not forward `device` to guided_info here (:737): its guides stay on the CPU.  The
+        # training feed (async_=True) keeps them on the device they were computed on.
+        guided_info = guides if async_ else [g.to("cpu") for g in guides]
+        return zs_dev.to(device), xs, guided_info, _posterior_out(mean, async_)
 
 
 class ClipSampler(DoubleSampler):
@@ -661,7 +734,7 @@ class ClipSampler(DoubleSampler):
                                 sl(i["leaves"], j), sl(i["post"], j), None)
         return {"t": t, "i": i, "n_local": nl}
 
-    def get_batch(self, device="cpu", batch_size=128, guide=False):
+    def get_batch(self, device="cpu", batch_size=128, guide=False, async_=False):
         r = self._sample_layout(batch_size, want_leaves=True, want_post=False)
         t, i = r["t"], r["i"]
         if guide:
@@ -669,16 +742,19 @@ class ClipSampler(DoubleSampler):
             ig, i_post, _ = self.i_model.guides_cls(i["leaves"])
             text_guided_info = [g.to(device) for g in tg]
             image_guided_info = [g.to(device) for g in ig]
-            t_pp = t_post.double().cpu().numpy()
-            i_pp = i_post.double().cpu().numpy()
+            t_pp = _posterior_out(t_post, async_)
+            i_pp = _posterior_out(i_post, async_)
         else:
             text_guided_info = image_guided_info = t_pp = i_pp = None
         return [t["leaves"].to(device), t["root"].to(device), text_guided_info, t_pp], \
                [i["leaves"].to(device), i["root"].to(device), image_guided_info, i_pp]
 
-    def get_Bayes(self, n_eval=10000, distributed=False, group=None):
+    def get_Bayes(self, n_eval=10000, distributed=False, group=None, lazy=False, keep_batch=False):
         """Bayes CLIP loss (reference :786-817).  ``distributed=True`` (Philox only) shards the pair index
-        over the initialised process group and all-reduces the 24-byte risk sums."""
+        over the initialised process group and all-reduces the 24-byte risk sums.  ``keep_batch=True`` also
+        materialises the int64 leaves of the evaluated batch on the device (the reference's get_Bayes builds the
+        whole batch through get_batch, :790) and leaves the layout in ``self.last_batch``.  ``lazy=True`` returns a
+        ``LazyRisk`` handle instead of blocking on the 24-byte device -> host read."""
         K, q = self.K, self.variable_type
         if distributed:
             if self.rng != "philox":
@@ -687,15 +763,19 @@ class ClipSampler(DoubleSampler):
             lo, hi = shard_range(n_eval, rank, world)
         else:
             lo, hi = 0, n_eval
-        r = self._sample_layout(n_eval, want_leaves=False, want_post=True, pair_lo=lo, pair_hi=hi)
+        r = self._sample_layout(n_eval, want_leaves=keep_batch, want_post=True, pair_lo=lo, pair_hi=hi)
+        self.last_batch = r if keep_batch else None
         nl = r["n_local"]
         sums = ops.new_sums(self.device)
         if nl > 0:
             ops.risk_clip(r["t"]["post"], r["i"]["post"], nl, K, q, sums=sums)
         if distributed:
             all_reduce_sums(sums, group)
-        mean, se = mean_se_from_sums(sums)
-        return np.float64(mean), np.float64(se)
+
+        def finish(s):
+            mean, se = mean_se_from_sums(s)
+            return np.float64(mean), np.float64(se)
+        return LazyRisk(sums, finish) if lazy else finish(sums)
 
 
 class ConditionalDenoiseSampler(DoubleSampler):
@@ -707,35 +787,43 @@ class ConditionalDenoiseSampler(DoubleSampler):
                          seedtree, device=device, rng=rng, seed=seed)
         self.sigma = sigma
 
-    def _run(self, batch_size):
-        """sample pair -> noise -> text BP_CLS -> ext -> image BP_DNS; everything stays on the device."""
-        _, text_tree, image_tree = self._paired_trees(batch_size)
+    def _noise(self, image_tree, batch_size):
+        """z = x + sigma * N(0, 1) for the image leaves (reference :867): host randn in parity mode, Philox on the device."""
         nLi = self.n_childs[1] ** self.n_layers[1]
         if self.rng == "numpy":
             noise = np.random.randn(nLi, batch_size) * self.sigma + np.asarray(image_tree.leaves_values)
-            z = torch.from_numpy(noise).to(self.device).T.to(torch.float32).contiguous()
-        else:
-            z = self.i_model.gauss_noise(image_tree._leaves, self.sigma, seed=self.seed ^ ops.IMAGE_SEED_XOR,
-                                         tree_offset=self.tree_offset - batch_size)
+            return torch.from_numpy(noise).to(self.device).T.to(torch.float32).contiguous()
+        return self.i_model.gauss_noise(image_tree._leaves, self.sigma, seed=self.seed ^ ops.IMAGE_SEED_XOR,
+                                        tree_offset=self.tree_offset - batch_size)
+
+    def _run(self, batch_size):
+        """sample pair -> noise -> text BP_CLS -> ext -> image BP_DNS; everything stays on the device."""
+        _, text_tree, image_tree = self._paired_trees(batch_size)
+        z = self._noise(image_tree, batch_size)
         t_post, t_hd = self.t_model.bp_cls(text_tree._leaves)
         mean = self.i_model.bp_dns(z, float(self.sigma), t_hd)
         return text_tree, image_tree, z, t_post, t_hd, mean
 
-    def get_batch(self, batch_size=128, device="cpu", guide=False):
-        text_tree, image_tree, z, t_post, t_hd, mean = self._run(batch_size)
+    def get_batch(self, batch_size=128, device="cpu", guide=False, async_=False):
         if guide:
-            tg, _, _ = self.t_model.guides_cls(text_tree._leaves)
-            ig, _ = self.i_model.guides_dns(z, float(self.sigma), t_hd)
+            # the guide kernels run the same BP and also return the posteriors: one pass per modality
+            _, text_tree, image_tree = self._paired_trees(batch_size)
+            z = self._noise(image_tree, batch_size)
+            tg, t_post, t_hd = self.t_model.guides_cls(text_tree._leaves)
+            ig, mean = self.i_model.guides_dns(z, float(self.sigma), t_hd)
             text_guided_info = [g.to(device) for g in tg]
             image_guided_info = [g.to(device) for g in ig]
         else:
+            text_tree, image_tree, z, t_post, t_hd, mean = self._run(batch_size)
             text_guided_info = image_guided_info = None
         return (text_tree._leaves.to(device), text_tree._root.to(device), text_guided_info,
-                t_post.T.double().cpu().numpy()), \
-               (z.to(device), image_tree._leaves.to(device), image_guided_info, mean.double().cpu().numpy())
+                _posterior_out(t_post.T, async_)), \
+               (z.to(device), image_tree._leaves.to(device), image_guided_info, _posterior_out(mean, async_))
 
-    def get_Bayes(self, n_eval=30000, distributed=False, group=None):
-        """Bayes MSE (reference :886-894): mean_b sum_leaf (m - x)^2 and np.std / sqrt(n)."""
+    def get_Bayes(self, n_eval=30000, distributed=False, group=None, lazy=False):
+        """Bayes MSE (reference :886-894): mean_b sum_leaf (m - x)^2 and np.std / sqrt(n).  Philox mode evaluates
+        any ``n_eval`` in pieces of ``bayes_chunk`` pairs (bounded workspace); ``distributed`` / ``lazy`` as in
+        ``ClipSampler.get_Bayes``."""
         if distributed:
             if self.rng != "philox":
                 raise ValueError("distributed get_Bayes needs rng='philox'")
@@ -747,14 +835,22 @@ class ConditionalDenoiseSampler(DoubleSampler):
         else:
             n_loc = n_eval
         sums = ops.new_sums(self.device)
-        if n_loc > 0:
+        if self.rng == "numpy":                              # parity mode: one draw like the reference
             _, image_tree, _, _, _, mean = self._run(n_loc)
             ops.risk_cdm(mean, image_tree._leaves, sums=sums)
+        else:                                                # Philox: bounded pieces, consecutive global tree indices
+            per_pair = self.i_model.dns_workspace_bytes(1) + 16 * (self.t_model.n_leaves + self.i_model.n_leaves)
+            for _, size in self._chunks(n_loc, per_pair):
+                _, image_tree, _, _, _, mean = self._run(size)
+                ops.risk_cdm(mean, image_tree._leaves, sums=sums)
         if distributed:
             self.tree_offset = base + n_eval
             all_reduce_sums(sums, group)
-        mean_v, se = mean_se_from_sums(sums)
-        return np.float64(mean_v), np.float64(se)
+
+        def finish(s):
+            mean_v, se = mean_se_from_sums(s)
+            return np.float64(mean_v), np.float64(se)
+        return LazyRisk(sums, finish) if lazy else finish(sums)
 
 
 class NextWordPredictSampler(DoubleSampler):
@@ -765,7 +861,7 @@ class NextWordPredictSampler(DoubleSampler):
         super().__init__(n_layers, n_childs, p_ys, p_flips, flip_scale, variable_type, translation_invariance,
                          seedtree, device=device, rng=rng, seed=seed)
 
-    def get_batch(self, batch_size=128, device="cpu", guide=False):
+    def get_batch(self, batch_size=128, device="cpu", guide=False, async_=False):
         _, text_tree, image_tree = self._paired_trees(batch_size)
         text_leaves = text_tree._leaves.to(device)
         if guide:
@@ -779,10 +875,11 @@ class NextWordPredictSampler(DoubleSampler):
             image_guided_info = text_guided_info = None
         return (text_leaves[:, :-1], text_leaves[:, 1:], text_guided_info, pp.to(device)), \
                (image_tree._leaves.to(device), image_tree._root.to(device), image_guided_info,
-                i_post.double().cpu().numpy())
+                _posterior_out(i_post, async_))
 
-    def get_Bayes(self, n_eval=30000, distributed=False, group=None):
-        """Bayes token CE (reference :931-942): float32 mean; "SE" = torch.std / sqrt(n_eval) (sic)."""
+    def get_Bayes(self, n_eval=30000, distributed=False, group=None, lazy=False):
+        """Bayes token CE (reference :931-942): float32 mean; "SE" = torch.std / sqrt(n_eval) (sic).  Chunked /
+        ``distributed`` / ``lazy`` as in ``ConditionalDenoiseSampler.get_Bayes``."""
         if distributed:
             if self.rng != "philox":
                 raise ValueError("distributed get_Bayes needs rng='philox'")
@@ -794,16 +891,22 @@ class NextWordPredictSampler(DoubleSampler):
         else:
             n_loc = n_eval
         sums = ops.new_sums(self.device)
-        if n_loc > 0:
-            _, text_tree, image_tree = self._paired_trees(n_loc)
+        nL = self.t_model.n_leaves
+        per_pair = 4 * (nL - 1) * self.variable_type + self.t_model.nwp_workspace_bytes(1) + 16 * (nL + self.i_model.n_leaves)
+        pieces = [(0, n_loc)] if self.rng == "numpy" else self._chunks(n_loc, per_pair)
+        for _, size in pieces:
+            _, text_tree, image_tree = self._paired_trees(size)
             _, i_hd = self.i_model.bp_cls(image_tree._leaves)
             pp = self.t_model.bp_nwp(text_tree._leaves, i_hd)
-            nL = self.t_model.n_leaves
             ops.risk_ce(pp, text_tree._leaves, sums=sums, target_stride=nL, target_offset=1, row_group=nL - 1)
         if distributed:
             self.tree_offset = base + n_eval
             all_reduce_sums(sums, group)
-        s1, s2, c = (float(x) for x in sums.tolist())
-        mean = s1 / c
-        var = max((s2 - c * mean * mean) / max(c - 1, 1), 0.0)          # torch.std is the unbiased estimator
-        return torch.tensor(mean, dtype=torch.float32), torch.tensor((var ** 0.5) / np.sqrt(n_eval), dtype=torch.float32)
+
+        def finish(s):
+            s1, s2, c = (float(x) for x in s.tolist())
+            mean = s1 / c
+            var = max((s2 - c * mean * mean) / max(c - 1, 1), 0.0)      # torch.std is the unbiased estimator
+            return (torch.tensor(mean, dtype=torch.float32),
+                    torch.tensor((var ** 0.5) / np.sqrt(n_eval), dtype=torch.float32))
+        return LazyRisk(sums, finish) if lazy else finish(sums)

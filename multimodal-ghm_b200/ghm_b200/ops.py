@@ -107,6 +107,12 @@ class GhmModel:
     def table_bytes(self):
         return int(self._lib.ghm_model_table_bytes(self._h))
 
+    def dns_workspace_bytes(self, batch):
+        return int(self._lib.ghm_bp_dns_workspace_bytes(self._h, int(batch)))
+
+    def nwp_workspace_bytes(self, batch):
+        return int(self._lib.ghm_bp_nwp_workspace_bytes(self._h, int(batch)))
+
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
@@ -165,21 +171,23 @@ class GhmModel:
         with _on(self.device):
             post = torch.empty((B, self.q), dtype=torch.float32, device=self.device)
             hd = torch.empty((B, self.q), dtype=torch.float32, device=self.device)
-            nws = self._lib.ghm_bp_cls_workspace_bytes(self._h, B)
-            ws = self._workspace(nws) if nws > 0 else None
+            ws = self._workspace(self._lib.ghm_bp_cls_workspace_bytes(self._h, B))
             check(self._lib.ghm_bp_cls(self._h, B, _ptr(leaves), _leaf_code(leaves), _ptr(post), _ptr(hd), _ptr(ws),
                                        _stream()))
         return post, hd
 
     # ---- K3 ---------------------------------------------------------------------------
     def _workspace(self, nbytes):
-        ws = getattr(self, "_ws", None)
-        if ws is None or ws.numel() < nbytes:
-            self._ws = ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
-        return ws
+        """Scratch for one call, allocated on the CURRENT stream through torch's caching allocator (stream-ordered
+        reuse: safe when the model is driven from several streams; nothing is held between calls)."""
+        nbytes = int(nbytes)
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device) if nbytes > 0 else None
 
-    def bp_dns(self, z, sigma, ext=None):
-        """z f32 [B,n_L], ext f32 [B,q] or None -> posterior mean f32 [B,n_L]  (reference BP_DNS, :467-523)."""
+    def bp_dns(self, z, sigma, ext=None, want_root_bu=False):
+        """z f32 [B,n_L], ext f32 [B,q] or None -> posterior mean f32 [B,n_L]  (reference BP_DNS, :467-523).
+
+        ``want_root_bu=True`` returns ``(mean, root_bu [B,q])``: the root's hd_message after the pass, i.e. the
+        max-shifted upward message plus ``ext`` without a re-shift (root bu aliases hd in the reference, :501-506)."""
         z = z.contiguous()
         B = z.shape[0]
         assert z.dtype == torch.float32 and z.shape[1] == self.n_leaves and z.device == self.device
@@ -189,8 +197,10 @@ class GhmModel:
         with _on(self.device):
             mean = torch.empty((B, self.n_leaves), dtype=torch.float32, device=self.device)
             ws = self._workspace(self._lib.ghm_bp_dns_workspace_bytes(self._h, B))
-            check(self._lib.ghm_bp_dns(self._h, B, _ptr(z), float(sigma), _ptr(ext), _ptr(mean), _ptr(ws), _stream()))
-        return mean
+            rbu = torch.empty((B, self.q), dtype=torch.float32, device=self.device) if want_root_bu else None
+            check(self._lib.ghm_bp_dns(self._h, B, _ptr(z), float(sigma), _ptr(ext), _ptr(mean), _ptr(rbu), _ptr(ws),
+                                       _stream()))
+        return (mean, rbu) if want_root_bu else mean
 
     # ---- K4 ---------------------------------------------------------------------------
     def bp_nwp(self, leaves, ext=None):

@@ -27,7 +27,8 @@ from . import ops
 from . import data_random_GHM as G
 from .sharding import mean_se_from_sums
 
-__all__ = ["clip_ood_sweep", "vlm_ood_sweep", "cdm_ood_sweep", "cdm_sigma_sweep", "write_reference_json", "DEFAULT_P_GRID"]
+__all__ = ["clip_ood_sweep", "vlm_ood_sweep", "cdm_ood_sweep", "cdm_sigma_sweep", "write_reference_json",
+           "write_bayes_checkpoint", "DEFAULT_P_GRID"]
 
 DEFAULT_P_GRID = tuple(int(p) for p in np.arange(2, 42, 2))          # percent, as the reference stores it
 
@@ -190,3 +191,22 @@ def write_reference_json(res, path, extra=None):
     with open(path, "w") as f:
         json.dump(out, f, indent=4)
     return out
+
+
+def write_bayes_checkpoint(path, sampler, n_eval=10000, state=None):
+    """Write the ``bayes`` key of the reference's training checkpoints from this path.
+
+    The reference's training scripts evaluate ``Bayes_loss, _ = sampler.get_Bayes(n_eval=10000)`` once and store it
+    in every ``checkpoint.pth`` (``training/train_CLIP.py:76,193-200``, ``train_CDNS.py:75,165-173``,
+    ``train_NWP.py:74``); the risk figures read only ``ckpt["bayes"]`` and ``ckpt["loss_history"]``
+    (``figures/eval-clip-risk.py:28-29``, ``eval-cdm-risk.py:28``, ``eval-vlm-risk.py:28``).  ``state`` carries the
+    caller's model / optimiser entries (``*_state_dict``, ``iter``, ``loss_history``, ``ploss_history`` ...); the
+    file is a plain ``torch.save`` dict, loadable with ``torch.load(path, weights_only=False)`` like the reference's.
+    Returns ``(bayes, bayes_std)``."""
+    bayes, bayes_std = sampler.get_Bayes(n_eval=n_eval)
+    ckpt = {"iter": 0, "loss_history": torch.zeros(0), "ploss_history": torch.zeros(0)}
+    if state:
+        ckpt.update(state)
+    ckpt["bayes"] = bayes
+    torch.save(ckpt, path)
+    return bayes, bayes_std

@@ -145,6 +145,6 @@ def gauss_noise(seed, tree_offset, batch, n_leaves):
     trees = np.arange(batch, dtype=np.uint64) + np.uint64(tree_offset)
     words = draw_words(seed, trees, 0, 2 * n_leaves, stream=1)   # two words per leaf
     w1, w2 = words[0::2], words[1::2]
-    u1 = ((w1 >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24)
+    u1 = (w1.astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -32)      # all 32 bits of the radial word
     u2 = ((w2 >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24)
     return (np.sqrt(np.float32(-2.0) * np.log(u1)) * np.cos(np.float32(2 * np.pi) * u2)).astype(np.float32)

@@ -36,8 +36,10 @@ def _cmp_guides(got, c, tag, n, atol=2e-5):
         ref = c[f"{tag}_guide{i}"]
         g = g.cpu().numpy()
         assert g.shape == ref.shape and g.dtype == np.float32, (i, g.shape, ref.shape)
-        fin = np.isfinite(ref) & (ref > -80.0)      # entries below e^-80 underflow in f32 by construction
-        np.testing.assert_allclose(g[fin], ref[fin], rtol=RTOL, atol=atol, err_msg=f"{tag} guide {i}")
+        # no mask: the kernels work in the log domain with a max shift, so entries far below e^-80 (leaf
+        # hd = -(z-k)^2 / 2 sigma^2 reaches -4400 at sigma = 0.1) are compared like every other one
+        assert np.isfinite(ref).all() and np.isfinite(g).all(), f"{tag} guide {i}: non-finite entries"
+        np.testing.assert_allclose(g, ref, rtol=RTOL, atol=atol, err_msg=f"{tag} guide {i}")
 
 
 @pytest.mark.parametrize("name", TREE_CASES)
@@ -47,8 +49,13 @@ def test_bp_dns_vs_reference_fixture(ops, name, tag):
     m = _model(ops, c)
     z = _bq(c["z"])
     ext = _bq(c["ext"]) if tag == "dnsx" else None
-    mean = m.bp_dns(z, c["sigma"], ext)
+    mean, root_bu = m.bp_dns(z, c["sigma"], ext, want_root_bu=True)
     np.testing.assert_allclose(mean.cpu().numpy(), c[f"{tag}_mean"].T, rtol=RTOL, atol=2e-6)
+    # root_node.hd_message after BP_DNS is hd + ext (root bu aliases hd, reference :501-506): the reference's root
+    # guide tensor (index L) broadcasts exactly that row over the leaves, identical halves
+    ref_root = c[f"{tag}_guide{c['L']}"][:, 0, :c["q"]]
+    assert np.array_equal(ref_root, c[f"{tag}_guide{c['L']}"][:, -1, c["q"]:])
+    np.testing.assert_allclose(root_bu.cpu().numpy(), ref_root, rtol=RTOL, atol=2e-5)
     guides, mean2 = m.guides_dns(z, c["sigma"], ext)       # independent log-domain implementation
     np.testing.assert_allclose(mean2.cpu().numpy(), c[f"{tag}_mean"].T, rtol=RTOL, atol=2e-6)
     _cmp_guides(guides, c, tag, 2 * c["L"] + 1)
@@ -109,6 +116,49 @@ def test_bp_dns_and_nwp_vs_oracle(ops, L, s, q, ti, B, sigma):
         gotp = m.bp_nwp(torch.from_numpy(np.ascontiguousarray(leaves.T)).cuda(), _bq(ext))
         np.testing.assert_allclose(gotp.cpu().numpy(), pp, rtol=RTOL, atol=1e-7)
     assert m.status() == 0
+
+
+@pytest.mark.parametrize("L,s,q,sigma", [(3, 3, 10, 0.1), (2, 4, 16, 0.3), (3, 2, 32, 0.25)])
+def test_dns_guides_with_outlier_observations(ops, L, s, q, sigma):
+    """Defined behaviour where float32 exp underflows: observations up to 3.5 away from every state at small sigma make
+    ALL leaf log-likelihoods fall below -87 (f32 exp underflow) while the reference's float64 exp(-0.5 d^2/sigma^2)
+    is still > 0 (d < 3.86 sigma-units of 0.1).  The log-domain kernels shift by the max before exponentiating, so every
+    guide entry is finite and matches the float64 oracle; the posterior mean matches too."""
+    from oracle import ghm_oracle as O
+    rng = np.random.RandomState(q + L)
+    np.random.seed(5 * q + L)
+    T = O.gen_transition(L, s, q, 0.15, 1.0, True)
+    B = 96
+    vals = O.sample_tree(T, L, s, q, B, root=rng.randint(0, q, size=B), U=rng.rand(O.n_edges(L, s), B))
+    z = vals[-1] + sigma * rng.randn(*vals[-1].shape)
+    out = rng.rand(*z.shape) < 0.2                                   # 20 % outliers beyond both ends of the state range
+    lim = min(3.5, 36.0 * sigma)                                     # keep the float64 oracle itself finite (hd > -700)
+    z[out] = np.where(rng.rand(out.sum()) < 0.5, -rng.uniform(1.5, lim, out.sum()), q - 1 + rng.uniform(1.5, lim, out.sum()))
+    ext = np.log(rng.dirichlet(np.ones(q), size=B).T)
+    ext -= ext.max(0)
+    # identical inputs on both sides: at d = 3.5, sigma = 0.1 the log-likelihood RATIO of neighbouring states moves by
+    # 100 * dz, so the float32 rounding of z (7e-7) alone would show up as 7e-5 in the messages
+    z = z.astype(np.float32).astype(np.float64)
+    ext = ext.astype(np.float32).astype(np.float64)
+    mean, hd, qd, bu = O.bp_dns(T, z, sigma, L, s, q, ext=ext)
+    ref = O.guides_dns(hd, qd, bu, L, s)
+    assert all(np.isfinite(r).all() for r in ref) and min(r.min() for r in ref) < -87.0
+    m = ops.GhmModel(T, L, s, q, device="cuda:0")
+    if q > 16:
+        with pytest.raises(RuntimeError):                            # guide tensors: register-resident kernels only (q <= 16)
+            m.guides_dns(_bq(z), sigma, _bq(ext))
+    else:
+        guides, mean2 = m.guides_dns(_bq(z), sigma, _bq(ext))
+        for i, (g, r) in enumerate(zip(guides, ref)):
+            g = g.cpu().numpy()
+            assert np.isfinite(g).all()
+            # the deepest tensor carries the leaves' bu = hd + log(T^T exp(bu_parent - qd)) - max, a difference of two
+            # numbers of magnitude |leaf hd| (<= 612 here): bounded by a few float32 ulps of that magnitude
+            atol = 2.5e-4 if i == 2 * L else 5e-5
+            np.testing.assert_allclose(g, r, rtol=1e-5, atol=atol, err_msg=f"guide {i}")
+        np.testing.assert_allclose(mean2.cpu().numpy(), mean.T, rtol=2e-5, atol=1e-5)
+    got = m.bp_dns(_bq(z), sigma, _bq(ext))
+    np.testing.assert_allclose(got.cpu().numpy(), mean.T, rtol=2e-5, atol=1e-5)
 
 
 def test_risk_cdm_and_ce_vs_numpy(ops):
