@@ -410,21 +410,42 @@ class LazyRisk:
     p_flip, figures/eval-clip-ood.py:73-79) enqueues evaluation k+1 before reading evaluation k, so the GPU never
     idles behind the host.  ``finish`` maps the three doubles to the method's return tuple."""
 
+    # Pinned landing slots are recycled: cudaHostAlloc per evaluation costs more than the evaluation's launches (and
+    # synchronises the device).  A slot is handed out again only after POOL further evaluations were issued.
+    POOL = 256
+    _slots = None
+    _next = 0
+
+    @classmethod
+    def _slot(cls):
+        if cls._slots is None:
+            cls._slots = torch.empty((cls.POOL, 3), dtype=torch.float64).pin_memory()
+        i = cls._next
+        cls._next = (i + 1) % cls.POOL
+        return cls._slots[i]
+
     def __init__(self, sums, finish):
-        self._host = torch.empty(3, dtype=torch.float64).pin_memory()
+        self._host = self._slot()
         self._host.copy_(sums, non_blocking=True)
         self._ev = torch.cuda.Event()
         self._ev.record(torch.cuda.current_stream(sums.device))
         self._finish = finish
         self._value = None
+        self._sums = None
 
     def done(self):
         return self._ev.query()
 
+    def sums(self):
+        """The raw {sum, sum of squares, count} as host floats (waits for the evaluation)."""
+        if self._sums is None:
+            self._ev.synchronize()
+            self._sums = [float(x) for x in self._host.tolist()]     # copied out: the slot is recycled later
+        return self._sums
+
     def result(self):
         if self._value is None:
-            self._ev.synchronize()
-            self._value = self._finish(self._host)
+            self._value = self._finish(torch.tensor(self.sums(), dtype=torch.float64))
         return self._value
 
 
@@ -542,17 +563,23 @@ class DoubleSampler(_SamplerBase):
             return np.random.choice(self.variable_type, size=batch_size)
         return None
 
-    def _paired_trees(self, batch_size):
+    def _paired_trees(self, batch_size, text_bp=False, image_bp=False):
+        """Shared-root text / image trees (:858-861).  Philox mode, q <= 16: ``text_bp`` / ``image_bp`` fuse BP_CLS into
+        the sampling launch of that modality (the leaves are absorbed from registers instead of being re-read) and
+        leave ``_post`` / ``_root_hd`` on the tree."""
         off = self._advance(batch_size) if self.rng == "philox" else 0
         if self.rng == "numpy":
             root = np.random.choice(self.variable_type, size=batch_size)
             text_tree = self._tree(0, batch_size, root=root)
             image_tree = self._tree(1, batch_size, root=root)
         else:
-            out = self.t_model.sample(batch_size, seed=self.seed, tree_offset=off, root_mode=ops.ROOT_UNIFORM)
+            fuse = self.variable_type <= 16
+            tb, ib = text_bp and fuse, image_bp and fuse
+            out = self.t_model.sample(batch_size, seed=self.seed, tree_offset=off, root_mode=ops.ROOT_UNIFORM,
+                                      want_post=tb, want_root_hd=tb)
             text_tree = _tree_from_device(self, 0, out, batch_size)
             iout = self.i_model.sample(batch_size, root=out["root"], seed=self.seed ^ ops.IMAGE_SEED_XOR,
-                                       tree_offset=off)
+                                       tree_offset=off, want_post=ib, want_root_hd=ib)
             image_tree = _tree_from_device(self, 1, iout, batch_size)
             root = None
         return root, text_tree, image_tree
@@ -598,7 +625,8 @@ def _tree_from_device(sampler, which, out, batch_size):
     t.dns_flag = t.cls_flag = False
     t.device, t.rng, t.seed, t.tree_offset = sampler.device, sampler.rng, sampler.seed, 0
     t._model_hint = mo
-    t._root_hd = t._root_hd_host = t._post = t._mean = t._dns_state = t._cls_guides = None
+    t._root_hd_host = t._mean = t._dns_state = t._cls_guides = None
+    t._post, t._root_hd = out.get("post"), out.get("root_hd")
     t._leaves, t._root, t._root_host, t._root_override = out["leaves"], out["root"], None, None
     t.T_value = [_RootLevel(t)] + [None] * (t.n_layer - 1) + [_LeafColumns(t._leaves)]
     t.Tree = None
@@ -798,9 +826,12 @@ class ConditionalDenoiseSampler(DoubleSampler):
 
     def _run(self, batch_size):
         """sample pair -> noise -> text BP_CLS -> ext -> image BP_DNS; everything stays on the device."""
-        _, text_tree, image_tree = self._paired_trees(batch_size)
+        _, text_tree, image_tree = self._paired_trees(batch_size, text_bp=True)
         z = self._noise(image_tree, batch_size)
-        t_post, t_hd = self.t_model.bp_cls(text_tree._leaves)
+        if text_tree._root_hd is not None:                   # Philox, q <= 16: BP_CLS ran inside the sampling launch
+            t_post, t_hd = text_tree._post, text_tree._root_hd
+        else:
+            t_post, t_hd = self.t_model.bp_cls(text_tree._leaves)
         mean = self.i_model.bp_dns(z, float(self.sigma), t_hd)
         return text_tree, image_tree, z, t_post, t_hd, mean
 
@@ -895,8 +926,10 @@ class NextWordPredictSampler(DoubleSampler):
         per_pair = 4 * (nL - 1) * self.variable_type + self.t_model.nwp_workspace_bytes(1) + 16 * (nL + self.i_model.n_leaves)
         pieces = [(0, n_loc)] if self.rng == "numpy" else self._chunks(n_loc, per_pair)
         for _, size in pieces:
-            _, text_tree, image_tree = self._paired_trees(size)
-            _, i_hd = self.i_model.bp_cls(image_tree._leaves)
+            _, text_tree, image_tree = self._paired_trees(size, image_bp=True)
+            i_hd = image_tree._root_hd
+            if i_hd is None:
+                _, i_hd = self.i_model.bp_cls(image_tree._leaves)
             pp = self.t_model.bp_nwp(text_tree._leaves, i_hd)
             ops.risk_ce(pp, text_tree._leaves, sums=sums, target_stride=nL, target_offset=1, row_group=nL - 1)
         if distributed:

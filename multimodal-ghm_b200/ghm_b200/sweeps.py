@@ -151,19 +151,26 @@ def cdm_ood_sweep(p_list=None, p_model=0.2, sigma=1.0, n_eval=10000, batch_size=
 
 
 def cdm_sigma_sweep(sigmas=(0.1, 0.25, 0.5, 1.0, 2.0, 4.0), p_flip=0.2, n_eval=65536, n_layers=(4, 4), n_childs=(3, 3),
-                    variable_type=10, seed=1234, device=None):
+                    variable_type=10, seed=1234, device=None, sampler=None):
     """Bayes denoising risk across diffusion noise levels (BASELINE config 3): ONE paired sample and ONE text BP_CLS
     give the external root message; per sigma: z = x + sigma * N(0, 1) (Philox normal), image BP_DNS conditioned on the
     text, risk sum_leaf (m - x)^2 (reference ConditionalDenoiseSampler.get_Bayes :886-894 at that sigma).  Everything
     stays on the device; the [n_sigma, 3] accumulator is copied back once.  Philox mode only (the reference has no
-    sigma loop whose NumPy stream could be mirrored)."""
+    sigma loop whose NumPy stream could be mirrored).  ``sampler`` re-uses a Philox-mode ConditionalDenoiseSampler (its
+    device tables) instead of constructing one."""
     q = variable_type
     py = [_uniform(q), _uniform(q)]
-    sampler = G.ConditionalDenoiseSampler(list(n_layers), list(n_childs), py, [p_flip, p_flip], sigma=1.0, variable_type=q,
-                                          device=device, rng="philox", seed=seed)
-    _, text_tree, image_tree = sampler._paired_trees(n_eval)
+    if sampler is None:
+        sampler = G.ConditionalDenoiseSampler(list(n_layers), list(n_childs), py, [p_flip, p_flip], sigma=1.0,
+                                              variable_type=q, device=device, rng="philox", seed=seed)
+    elif sampler.rng != "philox":
+        raise ValueError("cdm_sigma_sweep needs a Philox-mode sampler")
+    seed = sampler.seed
+    _, text_tree, image_tree = sampler._paired_trees(n_eval, text_bp=True)
     off = sampler.tree_offset - n_eval
-    _, t_hd = sampler.t_model.bp_cls(text_tree._leaves)
+    t_hd = text_tree._root_hd
+    if t_hd is None:
+        _, t_hd = sampler.t_model.bp_cls(text_tree._leaves)
     sums = torch.zeros((len(sigmas), 3), dtype=torch.float64, device=sampler.device)
     for k, sg in enumerate(sigmas):
         z = sampler.i_model.gauss_noise(image_tree._leaves, float(sg), seed=(seed ^ ops.IMAGE_SEED_XOR) + 7919 * (k + 1),

@@ -156,14 +156,28 @@ def test_sharded_risk_reduction_gloo_world2(tmp_path):
 
 
 def test_bench_reference_arm_prints_contract_line():
-    """`bench.py --impl reference` runs the CPU port and prints the JSON line the driver parses."""
+    """`bench.py --impl reference` runs the CPU arm (the unmodified reference under baseline/_ref when installed,
+    else the oracle port) and prints the JSON line the driver parses."""
     import json
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                           "--warmup", "1", "--cpu-n-eval", "300"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "trees/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "ghmclip", "data", "data_random_GHM.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_cpu_arms_reference_and_port_agree():
+    """baseline/cpu_arms.py: every task runs in both implementations and counts the same trees."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import cpu_arms as A
+    impls = ["port"] + (["reference"] if A.reference_available() else [])
+    for name, size in (("c2_clip", 40), ("c1_cdm", 16), ("c1_dns", 16), ("c3_sigma", 16), ("c4_nwp", 8),
+                       ("c4_nwp_guides", 4), ("c5_q10", 16), ("c5_pair", 16)):
+        trees = {impl: A.TASKS[name](impl, size, 3)[0] for impl in impls}
+        assert len(set(trees.values())) == 1 and trees["port"] > 0, (name, trees)
 
 
 def test_reference_json_writer_layout(tmp_path):

@@ -14,10 +14,17 @@ for p in [0.02 * (i + 1) for i in range(20)]:
     np.random.seed(42)
     grid.append((p, G.GenTransition(4, 3, 10, p, 1.0), G.GenTransition(4, 3, 10, p, 1.0)))
 n = 65536
+LAZY = "--lazy" in sys.argv
+pend = [None]
 def step(k):
     p, tt, it = grid[k % 20]
     s.reparameterize([p, p], transitions=(tt, it))
-    return s.get_Bayes(n_eval=n)
+    if not LAZY:
+        return s.get_Bayes(n_eval=n, keep_batch=True)
+    h = s.get_Bayes(n_eval=n, keep_batch=True, lazy=True)      # read evaluation k-1 while k runs (bench.py e2e)
+    if pend[0] is not None:
+        pend[0].result()
+    pend[0] = h
 for k in range(5): step(k)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
@@ -29,7 +36,7 @@ for k in range(100):
     p, tt, it = grid[k % 20]; s.reparameterize([p, p], transitions=(tt, it))
 torch.cuda.synchronize(); print("reparameterize %.1f us" % ((time.perf_counter() - t0) / 100 * 1e6))
 t0 = time.perf_counter()
-for k in range(100): s.get_Bayes(n_eval=n)
+for k in range(100): s.get_Bayes(n_eval=n, keep_batch=True, lazy=LAZY)
 torch.cuda.synchronize(); print("get_Bayes %.1f us" % ((time.perf_counter() - t0) / 100 * 1e6))
 pr = cProfile.Profile(); pr.enable()
 for k in range(200): step(k)
