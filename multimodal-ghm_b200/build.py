@@ -9,6 +9,7 @@ import concurrent.futures as cf
 import glob
 import hashlib
 import os
+import re
 import subprocess
 import sys
 
@@ -22,10 +23,27 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
 
+_INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+
+
+def _closure(path, seen):
+    """Transitive closure of the quoted includes of ``path`` (only headers of this repo are quoted)."""
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return
+    seen.add(path)
+    with open(path, "r", errors="replace") as fh:
+        text = fh.read()
+    for inc in _INC.findall(text):
+        _closure(os.path.join(os.path.dirname(path), inc), seen)
+
+
 def _deps_hash(src):
+    """Hash of the source, the headers it (transitively) includes and the flags: a header edit rebuilds only its users."""
+    seen = set()
+    _closure(src, seen)
     h = hashlib.sha1()
-    for f in [src] + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
-            sorted(glob.glob(os.path.join(HERE, "..", "include", "*.h"))):
+    for f in sorted(seen):
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(FLAGS).encode())

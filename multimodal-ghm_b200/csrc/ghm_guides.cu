@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "ghm_vec2.cuh"
+#include "ghm_wide_lvl.cuh"
 
 #define GD_NT 128
 
@@ -869,14 +870,26 @@ extern "C" int ghm_guides_cls(const ghm_model_t* m, int64_t B, const void* leave
     float* HD = guides[L - 1];
     if (n_int > (int64_t)d.n_leaves) return ghm_fail(GHM_EUNSUP, "unexpected tree shape");
     a.HD = HD;
-    int rc = dispatch_q(d.q, [&](auto Qc) -> int {
-        constexpr int Q = decltype(Qc)::value;
+    int rc;
+    if (d.QW) {                                                // 16 < q <= 256: one warp per (tree, node) row (ghm_wide_lvl.cuh)
+        WLvlArgs wa{};
+        wa.B = B; wa.leaves = leaves; wa.leaf_dtype = leaf_dtype; wa.HD = HD; wa.n_nodes = (int)n_int;
+        wa.post = post; wa.root_hd = root_hd;
+        rc = GHM_OK;
         for (int l = d.L - 1; l >= 0; --l) {
-            k_lvl_cls<Q><<<lvl_grid(d, B, l), GD_NT, 0, st>>>(d, a, l);
+            k_wl_cls<<<wl_grid(B * d.spow[l]), WL_NT, (size_t)(WL_NT / 32) * d.QW * sizeof(float), st>>>(d, wa, l);
             GHM_CHECK_LAUNCH();
         }
-        return GHM_OK;
-    });
+    } else {
+        rc = dispatch_q(d.q, [&](auto Qc) -> int {
+            constexpr int Q = decltype(Qc)::value;
+            for (int l = d.L - 1; l >= 0; --l) {
+                k_lvl_cls<Q><<<lvl_grid(d, B, l), GD_NT, 0, st>>>(d, a, l);
+                GHM_CHECK_LAUNCH();
+            }
+            return GHM_OK;
+        });
+    }
     if (rc) return rc;
     // guides[j] <- depth L-1-j, j = 0..L-2, read from HD (inside guides[L-1]); then the root level from root_hd
     {
@@ -956,18 +969,35 @@ extern "C" int ghm_guides_dns(const ghm_model_t* m, int64_t B, const float* z, f
     if (!workspace)
         return ghm_fail(GHM_EINVAL, "ghm_guides_dns: the level-synchronous path needs a workspace of 3*B*nodes*q floats "
                                     "(guide pointers null / not 8-byte aligned, or the tree does not fit shared memory)");
-    int rc = dispatch_q(d.q, [&](auto Qc) -> int {
-        constexpr int Q = decltype(Qc)::value;
+    int rc;
+    if (d.QW) {                                                // 16 < q <= 256: one warp per (tree, node) row (ghm_wide_lvl.cuh)
+        WLvlArgs wa{};
+        wa.B = B; wa.z = z; wa.sigma = sigma; wa.ext = ext; wa.HD = HD; wa.QD = QD; wa.BU = BU; wa.n_nodes = (int)nn;
+        wa.mean = mean;
+        const size_t dyn = (size_t)(WL_NT / 32) * d.QW * sizeof(float);
+        rc = GHM_OK;
         for (int l = d.L; l >= 0; --l) {
-            k_lvl_dns_up<Q><<<lvl_grid(d, B, l), GD_NT, 0, st>>>(d, a, l);
+            k_wl_dns_up<<<wl_grid(B * d.spow[l]), WL_NT, dyn, st>>>(d, wa, l);
             GHM_CHECK_LAUNCH();
         }
         for (int l = 1; l <= d.L; ++l) {
-            k_lvl_dns_down<Q><<<lvl_grid(d, B, l), GD_NT, 0, st>>>(d, a, l);
+            k_wl_dns_down<<<wl_grid(B * d.spow[l]), WL_NT, dyn, st>>>(d, wa, l);
             GHM_CHECK_LAUNCH();
         }
-        return GHM_OK;
-    });
+    } else {
+        rc = dispatch_q(d.q, [&](auto Qc) -> int {
+            constexpr int Q = decltype(Qc)::value;
+            for (int l = d.L; l >= 0; --l) {
+                k_lvl_dns_up<Q><<<lvl_grid(d, B, l), GD_NT, 0, st>>>(d, a, l);
+                GHM_CHECK_LAUNCH();
+            }
+            for (int l = 1; l <= d.L; ++l) {
+                k_lvl_dns_down<Q><<<lvl_grid(d, B, l), GD_NT, 0, st>>>(d, a, l);
+                GHM_CHECK_LAUNCH();
+            }
+            return GHM_OK;
+        });
+    }
     if (rc || !guides) return rc;
     // (hd|qd) depth L..1 ; root (hd|bu) ; (hd|qd|bu) depth 1..L      (reference :554-590) -- one launch
     ExpandAll e;

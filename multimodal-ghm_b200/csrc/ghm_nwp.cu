@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "ghm_vec2.cuh"
+#include "ghm_wide_lvl.cuh"
 
 #define NWP_NT 128
 #define NWP_MAX_GUIDES (2 * GHM_MAX_LEVELS + 1)
@@ -539,6 +540,28 @@ static int dispatch_nwp(const ghm_model* m, const NwpArgs& a, cudaStream_t st) {
     }
 }
 
+// wide q (ghm_wide_lvl.cuh): log-domain, warp per row; finished-subtree messages in the same [B][n_int][q] workspace
+static int launch_nwp_wide(const ghm_model* m, const NwpArgs& a, float* const* guides, cudaStream_t st) {
+    const GhmDev& d = m->d;
+    WNwpArgs w{};
+    w.B = a.B; w.leaves = a.leaves; w.leaf_dtype = a.leaf_dtype; w.ext = a.ext; w.pp = a.pp; w.full = a.full; w.n_int = a.n_int;
+    w.guide = guides ? 1 : 0;
+    if (guides)
+        for (int i = 0; i < 2 * d.L + 1; ++i) w.guides[i] = guides[i];
+    const int warps = WL_NT / 32;
+    for (int l = d.L - 1; l >= 1; --l) {
+        k_wl_nwp_full<<<wl_grid(a.B * d.spow[l]), WL_NT, (size_t)warps * d.QW * sizeof(float), st>>>(d, w, l);
+        GHM_CHECK_LAUNCH();
+    }
+    const size_t dyn = (size_t)warps * (size_t)(d.QW + 2 * (d.L - 1) * d.QW) * sizeof(float);
+    if (dyn > 200 * 1024)
+        return ghm_fail(GHM_EUNSUP, "wide nwp kernel needs %zu bytes of shared memory (L=%d q=%d)", dyn, d.L, d.q);
+    GHM_CUDA_TRY(cudaFuncSetAttribute(k_wl_nwp_pos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    k_wl_nwp_pos<<<wl_grid(a.B * (int64_t)(d.n_leaves - 1)), WL_NT, dyn, st>>>(d, w);
+    GHM_CHECK_LAUNCH();
+    return GHM_OK;
+}
+
 static int64_t nwp_ws_bytes(const ghm_model_t* m, int64_t B) {
     if (!m || B <= 0) return 16;
     return std::max<int64_t>(16, B * (int64_t)(1 + m->d.edge_off[m->d.L]) * m->d.q * (int64_t)sizeof(float));
@@ -557,7 +580,9 @@ static int nwp_common(const ghm_model_t* m, int64_t B, const void* leaves, int l
     a.B = B; a.leaves = leaves; a.leaf_dtype = leaf_dtype; a.ext = ext; a.pp = pp;
     a.full = (float*)workspace; a.n_int = 1 + m->d.edge_off[m->d.L];
     int rc;
-    if (guides) {
+    if (m->d.QW) {                                             // 16 < q <= 256: one warp per (tree, node / position) row
+        rc = launch_nwp_wide(m, a, guides, (cudaStream_t)stream);
+    } else if (guides) {
         for (int i = 0; i < 2 * m->d.L + 1; ++i) a.guides[i] = guides[i];
         rc = dispatch_nwp<true>(m, a, (cudaStream_t)stream);
     } else {

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(PAR_NT) k_sample_parity(const GhmDev d, const 
 }
 
 #ifdef GHM_TREE_PROBE   // development aid: compile one instantiation only (nvcc -DGHM_TREE_PROBE=2 -cubin)
-template __global__ void k_tree2<10, 3, GHM_TREE_PROBE, MODE_PHILOX, true, true, true, 1536>(
+template __global__ void k_tree_fast<10, 3, MODE_PHILOX, true, 1536>(
     const __grid_constant__ GhmDev, const __grid_constant__ TreeArgs, const __grid_constant__ TabParam<1536>);
 #endif
 

@@ -1,0 +1,338 @@
+// ghm_tree_fast.cuh -- the software-pipelined fast variant of the fused sampler + root-posterior kernel.
+//
+// Same contract, same Philox counter layout and same arithmetic as k_tree2 (ghm_tree_kernel.cuh; reference
+// GHMTree.gen_values :145-165 and GHMTree.BP_CLS :185-221 of src/ghmclip/data/data_random_GHM.py), specialised
+// for what the hot configurations are: translation-invariant tables, s in {2,3,4}, L >= 3, two trees per thread,
+// whole leaf rows staged flat, T^T tables in the constant bank.
+//
+// What is different from k_tree2 (ncu, profiles/r02b_*: the old loop was LATENCY bound -- 3.5 warps per scheduler,
+// issue slots 63 % busy, FMA-heavy pipe 54 %, the rest "short scoreboard" / "wait" stalls on the dependent chain
+// alias LDS -> alias LDS -> T^T row LDS -> FMUL2 of every node):
+//   * the loop is software pipelined over the depth-(L-1) nodes: one iteration holds three independent chains
+//     -- the Philox block of node j+2 (IMAD.WIDE chain, FMA-heavy pipe), the draws + leaf-row products of node
+//     j+1 (LDS chain, ALU pipe), and the BP climb of node j (packed FFMA2 with constant-bank operands) -- so
+//     the leaf-row product of the next node is in registers before the climb that needs it starts;
+//   * no odometer: child digits of the rarely taken deep steps come from `j / s^k` by the host's multiply-high
+//     magics (uniform datapath), the two hot steps use running counters.
+#pragma once
+
+template <int Q, int S, int MODE, bool BP, int NW>
+__global__ void __launch_bounds__(T2_NT, 4)
+k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a, const __grid_constant__ TabParam<NW> tab) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int TPT = 2, NT = T2_NT, H = Q / 2, QS = (Q + 3) / 4 * 4, WTREES = 32 * TPT;
+    constexpr bool SPARE = (S & 3) != 0;                         // node j is drawn from the spare word of its leaf block
+    constexpr bool PHILOX = MODE == MODE_PHILOX;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = d.L, q = d.q, nL = d.n_leaves;                 // L >= 3 (host)
+    const int64_t warp_tree0 = ((int64_t)blockIdx.x * T2_WARPS + warp) * WTREES;
+    const bool warp_has_work = warp_tree0 < a.B;
+
+    // ---- carve shared memory (same layout as k_tree2) -------------------------------------
+    size_t off = 0;
+    const float* tt_leaf0 = nullptr;
+    const uint32_t* AL = d.alias;
+    if (BP) {                                                    // leaf-level T^T rows are gathered per lane by leaf state
+        const int first = d.mat_off[L];
+        const int words = S * Q * QS;
+        float* s1 = reinterpret_cast<float*>(smem + off); off += (size_t)words * 4;
+        const float* src = d.TTp + (size_t)first * Q * QS;
+        for (int i = tid; i < words; i += NT) s1[i] = src[i];
+        tt_leaf0 = s1;
+    }
+    if (PHILOX) {
+        const int words = d.n_mat * q * q;
+        uint32_t* s2 = reinterpret_cast<uint32_t*>(smem + off); off += ((size_t)words * 4 + 15) / 16 * 16;
+        for (int i = tid; i < words; i += NT) s2[i] = d.alias[i];
+        AL = s2;
+    }
+    const int n_deep = L - 2;                                    // ancestors kept in shared memory: depths 0 .. L-3
+    f2* ACC = reinterpret_cast<f2*>(smem + off);                 // [n_deep][H][TPT][NT]
+    if (BP) off += (size_t)n_deep * H * TPT * NT * sizeof(f2);
+    const int n_rng = n_deep + (SPARE ? 0 : 1);                  // levels 1 .. L-2 (+ L-1 when it has no spare word)
+    uint32_t* RNG = reinterpret_cast<uint32_t*>(smem + off);     // [n_rng][3][TPT][NT]  words 1..3 of the cached Philox blocks
+    if (PHILOX) off += (size_t)n_rng * 3 * TPT * NT * 4;
+    uint8_t* VAL = smem + off;                                   // [n_deep][TPT][NT] states of the path nodes at depths 0 .. L-3
+    if (PHILOX) off += ((size_t)n_deep * TPT * NT + 15) / 16 * 16;
+    const bool use_stage = (a.leaves != nullptr);
+    uint8_t* stage = smem + off + (size_t)warp * a.stage_bytes;
+    __syncthreads();
+    if (!warp_has_work) return;
+
+    const int n1 = d.spow[L - 1];
+    bool active[TPT];
+    uint64_t tree[TPT];
+    int64_t bt[TPT];
+    int srow[TPT];
+#pragma unroll
+    for (int t = 0; t < TPT; ++t) {
+        bt[t] = warp_tree0 + 32 * t + lane;
+        active[t] = bt[t] < a.B;
+        const int64_t bc = active[t] ? bt[t] : a.B - 1;          // tail threads shadow the last tree and never write
+        tree[t] = a.tree_offset + (uint64_t)bc;
+        srow[t] = (32 * t + lane) * nL;
+    }
+    if (!PHILOX) stage_load_flat(stage, WTREES, a.leaves, a.leaf_dtype, warp_tree0, a.B, nL, lane, q, d.status);
+
+    // ---- root ---------------------------------------------------------------------------
+    int xpar[TPT];                                               // state of the depth-(L-2) parent of the node being drawn
+#pragma unroll
+    for (int t = 0; t < TPT; ++t) xpar[t] = 0;
+    if (PHILOX) {
+#pragma unroll
+        for (int t = 0; t < TPT; ++t) {
+            const int64_t bc = active[t] ? bt[t] : a.B - 1;
+            int x0;
+            if (a.root_mode == GHM_ROOT_GIVEN && bc < a.n_given) {
+                int64_t r = a.root_in[bc];
+                if (r < 0 || r >= q) { atomicOr(d.status, 1); r = r < 0 ? 0 : q - 1; }
+                x0 = (int)r;
+            } else {
+                const bool shared = a.root_mode == GHM_ROOT_SHARED && bc < a.n_given;
+                const uint4 rb = ghm_rng_block(shared ? a.root_seed : a.seed, tree[t], 0u, 0u, GHM_STREAM_TREE);
+                const uint32_t* rc = a.root_mode == GHM_ROOT_PRIOR ? d.root_cdfu_prior : d.root_cdfu_unif;
+                int cnt = 0;
+                for (int k = 0; k < q - 1; ++k) cnt += (rb.x >= __ldg(rc + k)) ? 1 : 0;
+                x0 = cnt;
+            }
+            VAL[t * NT + tid] = (uint8_t)x0;
+            if (a.root_out && active[t]) a.root_out[bt[t]] = x0;
+        }
+    }
+
+    const uint32_t* alias_leaf0 = AL + (size_t)d.mat_off[L] * q * q;
+    const int base0 = a.base0, base1 = a.base1;                  // (L-2)*s, (L-3)*s: constant-bank matrix index of the two hottest climb steps
+
+    // (re)draw the ancestors of node jn at depths 1 .. L-2 that changed: depth l changes iff s^(L-1-l) divides jn
+    auto redraw_ancestors = [&](int jn) {
+        for (int l = 1; l <= L - 2; ++l) {
+            const int idx = ghm_div_pow(jn, L - 1 - l, d);
+            if (idx * d.spow[L - 1 - l] != jn) continue;
+            const int c = idx - (idx / S) * S;
+            const uint32_t* arow = AL + (size_t)((l - 1) * S + c) * q * q;
+#pragma unroll
+            for (int t = 0; t < TPT; ++t) {
+                uint32_t* rl = RNG + (size_t)((l - 1) * 3 * TPT + t) * NT + tid;
+                uint32_t r;
+                if ((idx & 3) == 0) {
+                    const uint4 rb = ghm_rng_block(a.seed, tree[t], (uint32_t)l, (uint32_t)(idx >> 2), GHM_STREAM_TREE);
+                    rl[0] = rb.y; rl[TPT * NT] = rb.z; rl[2 * TPT * NT] = rb.w;
+                    r = rb.x;
+                } else {
+                    r = rl[((idx & 3) - 1) * TPT * NT];
+                }
+                const int xp = VAL[((l - 1) * TPT + t) * NT + tid];
+                const int x = ghm_draw_alias(arow + xp * q, r, q);
+                if (l < L - 2) VAL[(l * TPT + t) * NT + tid] = (uint8_t)x; else xpar[t] = x;
+            }
+        }
+    };
+
+    // draw node jn (child cjn of its parent) and its S leaves, stage the leaves, and form the product of the leaf
+    // rows hout = prod_c T_c^T[x_c, :]  (reference :191-196 in the linear domain)
+    auto sample_node = [&](int jn, int cjn, const uint4 (&rb)[TPT], f2 (&hout)[TPT][H]) {
+        int xc[TPT];
+        if (PHILOX) {
+            const uint32_t* arow = AL + (size_t)(base0 + cjn) * q * q;
+#pragma unroll
+            for (int t = 0; t < TPT; ++t) {
+                uint32_t r;
+                if (SPARE) {
+                    r = ghm_pick(rb[t], S & 3);
+                } else {                                         // s == 4: word jn & 3 of block (level L-1, jn >> 2)
+                    uint32_t* rl = RNG + (size_t)((L - 2) * 3 * TPT + t) * NT + tid;
+                    if ((jn & 3) == 0) {
+                        const uint4 rj = ghm_rng_block(a.seed, tree[t], (uint32_t)(L - 1), (uint32_t)(jn >> 2), GHM_STREAM_TREE);
+                        rl[0] = rj.y; rl[TPT * NT] = rj.z; rl[2 * TPT * NT] = rj.w;
+                        r = rj.x;
+                    } else {
+                        r = rl[((jn & 3) - 1) * TPT * NT];
+                    }
+                }
+                xc[t] = ghm_draw_alias(arow + xpar[t] * q, r, q);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < S; ++c) {
+#pragma unroll
+            for (int t = 0; t < TPT; ++t) {
+                int x;
+                if (PHILOX) {
+                    x = ghm_draw_alias(alias_leaf0 + (c * q + xc[t]) * q, ghm_pick(rb[t], c), q);
+                    if (use_stage) stage[srow[t] + jn * S + c] = (uint8_t)x;
+                } else {
+                    x = stage[srow[t] + jn * S + c];
+                }
+                if (BP) {
+                    f2 row[H];
+                    f2_load_row<Q>(tt_leaf0 + (c * Q + x) * QS, row);
+#pragma unroll
+                    for (int i = 0; i < H; ++i) hout[t][i] = c == 0 ? row[i] : f2_mul(hout[t][i], row[i]);
+                }
+            }
+        }
+    };
+
+    f2 msg[TPT][H], accT[TPT][H];
+#pragma unroll
+    for (int t = 0; t < TPT; ++t)
+#pragma unroll
+        for (int i = 0; i < H; ++i) { msg[t][i] = make_float2(0.f, 0.f); accT[t][i] = make_float2(0.f, 0.f); }
+
+    // One climb step: u = T m for both trees, times the parked product of the earlier siblings; park it again (more
+    // siblings to come) or rescale and keep climbing.  A == nullptr: register accumulator.
+    auto climb_step = [&](const float* __restrict__ Tm, bool has_prev, bool last, f2* A) -> bool {
+        f2 u[TPT][H];
+        f2_matvec_up2<Q, QS>(Tm, msg[0], msg[1], u[0], u[1]);
+        if (has_prev) {
+#pragma unroll
+            for (int t = 0; t < TPT; ++t)
+#pragma unroll
+                for (int i = 0; i < H; ++i) u[t][i] = f2_mul(u[t][i], A ? A[(i * TPT + t) * NT] : accT[t][i]);
+        }
+        if (!last) {
+#pragma unroll
+            for (int t = 0; t < TPT; ++t)
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    if (A) A[(i * TPT + t) * NT] = u[t][i]; else accT[t][i] = u[t][i];
+                }
+            return false;
+        }
+#pragma unroll
+        for (int t = 0; t < TPT; ++t) {
+#pragma unroll
+            for (int i = 0; i < H; ++i) msg[t][i] = u[t][i];
+            f2_normalize<Q>(msg[t]);
+        }
+        return true;
+    };
+
+    // the BP climb of node j, whose leaf-row product is h
+    auto climb = [&](int j, int cj, int c1, const f2 (&h)[TPT][H]) {
+#pragma unroll
+        for (int t = 0; t < TPT; ++t) {
+#pragma unroll
+            for (int i = 0; i < H; ++i) msg[t][i] = h[t][i];
+            f2_normalize<Q>(msg[t]);
+        }
+        // the two hottest steps (every node / every s-th node) read their table through running offsets that feed
+        // nothing but the constant-bank address, so they stay in UNIFORM registers (LDCU.64 + FFMA2 with a UR operand)
+        bool up = climb_step(tab.v + (base0 + cj) * (Q * QS), cj != 0, cj == S - 1, nullptr);
+        if (up) up = climb_step(tab.v + (base1 + c1) * (Q * QS), c1 != 0, c1 == S - 1, ACC + (size_t)(L - 3) * H * TPT * NT + tid);
+        if (up && L >= 4) {
+            f2* A = ACC + (size_t)(L - 4) * H * TPT * NT + tid;
+            for (int l = L - 3; l > 0; --l) {
+                const int idx = ghm_div_pow(j, L - 1 - l, d);    // index of the path node at depth l
+                const int c = idx - (idx / S) * S;
+                if (!climb_step(tab.v + ((l - 1) * S + c) * (Q * QS), c != 0, c == S - 1, A)) break;
+                A -= H * TPT * NT;
+            }
+        }
+    };
+
+    // ---- prologue: ancestors + node 0 ---------------------------------------------------
+    uint4 rbA[TPT], rbB[TPT];                                    // Philox blocks of the leaves of nodes j+1 / j+2
+    f2 hcur[TPT][H], hnext[TPT][H];
+    if (PHILOX) {
+        redraw_ancestors(0);
+#pragma unroll
+        for (int t = 0; t < TPT; ++t) {
+            rbA[t] = ghm_rng_block(a.seed, tree[t], (uint32_t)L, 0u, GHM_STREAM_TREE);
+            rbB[t] = ghm_rng_block(a.seed, tree[t], (uint32_t)L, 1u, GHM_STREAM_TREE);
+        }
+    }
+    sample_node(0, 0, rbA, hcur);
+#pragma unroll
+    for (int t = 0; t < TPT; ++t) rbA[t] = rbB[t];               // block of node 1
+
+    int cj = 0, c1 = 0;                                          // j mod s, (j / s) mod s
+    for (int j = 0; j < n1 - 1; ++j) {
+        const int jn = j + 1;
+        const int cjn = cj + 1 == S ? 0 : cj + 1;
+        if (PHILOX && cjn == 0) redraw_ancestors(jn);
+        // ---- one straight-line block: Philox of node j+2, draws + leaf rows of node j+1, BP climb step of node j ----
+        // (measured: guarding the sampling half with `jn < n1` instead of peeling the last climb costs 4 %)
+        if (PHILOX) {
+#pragma unroll
+            for (int t = 0; t < TPT; ++t)                        // (one block past the end is computed and dropped)
+                rbB[t] = ghm_rng_block(a.seed, tree[t], (uint32_t)L, (uint32_t)(jn + 1), GHM_STREAM_TREE);
+        }
+        sample_node(jn, cjn, rbA, hnext);
+        if (BP) climb(j, cj, c1, hcur);
+#pragma unroll
+        for (int t = 0; t < TPT; ++t) {
+            rbA[t] = rbB[t];
+#pragma unroll
+            for (int i = 0; i < H; ++i) hcur[t][i] = hnext[t][i];
+        }
+        cj = cjn;
+        if (cjn == 0) c1 = c1 + 1 == S ? 0 : c1 + 1;
+    }
+    if (BP) climb(n1 - 1, cj, c1, hcur);
+
+    if (PHILOX && use_stage) stage_flush_flat(stage, WTREES, a.leaves, a.leaf_dtype, warp_tree0, a.B, nL, lane);
+
+    // ---- root outputs (reference :213-217; root_node.hd_message is the shifted log-likelihood) --
+    if (BP) {
+#pragma unroll
+        for (int t = 0; t < TPT; ++t) {
+            if (!active[t]) continue;
+            const int64_t b = bt[t];
+            if (a.root_hd) {
+#pragma unroll
+                for (int k = 0; k < Q; ++k)
+                    if (k < q) a.root_hd[b * q + k] = logf(f2_elem<Q>(msg[t], k));
+            }
+            if (a.post) {
+                float w[Q], sum = 0.f;
+#pragma unroll
+                for (int k = 0; k < Q; ++k) { w[k] = f2_elem<Q>(msg[t], k) * __ldg(d.py + k); sum += w[k]; }
+                const float inv = 1.0f / sum;
+#pragma unroll
+                for (int k = 0; k < Q; ++k)
+                    if (k < q) a.post[b * q + k] = w[k] * inv;
+            }
+        }
+    }
+}
+
+// host side: same shared-memory carve as the kernel above
+template <int Q, int S, int MODE, bool BP, int NW>
+static int launch_tree_fast(const ghm_model* m, const TreeArgs& a0, cudaStream_t st) {
+    const GhmDev& d = m->d;
+    TreeArgs a = a0;
+    constexpr int QS = (Q + 3) / 4 * 4, WTREES = 64;
+    const int n_deep = d.L - 2;
+    size_t dyn = 0;
+    if (BP) dyn += (size_t)S * Q * QS * 4;
+    if (MODE == MODE_PHILOX) dyn += ((size_t)d.n_mat * d.q * d.q * 4 + 15) / 16 * 16;
+    if (BP) dyn += (size_t)n_deep * (Q / 2) * 2 * T2_NT * sizeof(float2);
+    if (MODE == MODE_PHILOX) {
+        const int n_rng = n_deep + ((S & 3) != 0 ? 0 : 1);
+        dyn += (size_t)n_rng * 3 * 2 * T2_NT * 4 + ((size_t)n_deep * 2 * T2_NT + 15) / 16 * 16;
+    }
+    a.chunk_j = d.spow[d.L - 1]; a.stage_stride = 0; a.stage_bytes = 0;
+    a.base0 = (d.L - 2) * d.s; a.base1 = (d.L - 3) * d.s;
+    if (a.leaves) {
+        a.stage_stride = d.n_leaves;
+        a.stage_bytes = (int)(((size_t)WTREES * d.n_leaves + 15) / 16 * 16);
+    }
+    dyn += (size_t)a.stage_bytes * T2_WARPS;
+    if (dyn > 200 * 1024)
+        return ghm_fail(GHM_EUNSUP, "tree kernel needs %zu bytes of shared memory (L=%d s=%d q=%d)", dyn, d.L, d.s, d.q);
+    const int64_t trees_per_cta = (int64_t)T2_WARPS * WTREES;
+    const unsigned grid = (unsigned)((a.B + trees_per_cta - 1) / trees_per_cta);
+    TabParam<NW> tab;                                              // by-value table parameter (copied at launch)
+    tab.v[0] = 0.f;
+    if (BP) {
+        const size_t words = (size_t)d.n_mat * Q * QS;
+        if (words > (size_t)NW) return ghm_fail(GHM_EUNSUP, "internal: constant table overflow");
+        memcpy(tab.v, m->h_TTp, words * sizeof(float));
+    }
+    auto kern = k_tree_fast<Q, S, MODE, BP, NW>;
+    GHM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    kern<<<grid, T2_NT, dyn, st>>>(d, a, tab);
+    GHM_CHECK_LAUNCH();
+    return GHM_OK;
+}

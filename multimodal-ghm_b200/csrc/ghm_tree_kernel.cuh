@@ -301,16 +301,8 @@ k_tree2(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a, co
         for (int i = 0; i < H; ++i) { msg[t][i] = make_float2(0.f, 0.f); accT[t][i] = make_float2(0.f, 0.f); }
 
     int chunk_base = 0, chunk_left = a.chunk_j;                  // row-chunk staging only
-    // Path bookkeeping.  Fast variants (S > 0, translation-invariant tables): the base-s digits of j -- the child
-    // index of the path node at each depth -- are an odometer packed 4 bits per level in a 64-bit value, so every
-    // table address is built from shifts/ands of a loop counter and the compiler keeps it in UNIFORM registers
-    // (LDCU + UR operands; an integer division would force the vector datapath).  Generic variant: divisions.
-    constexpr bool FAST = S > 0;
-    unsigned long long D = 0;                                    // digit of depth l at bits [4l, 4l+4), l = 1 .. L-1
     int tz = L > 2 ? L - 2 : 0;                                  // ancestors to (re)draw before node j: depths L-1-tz .. L-2
     int cj = 0;                                                  // j mod s  (child index of node j under its parent)
-    const int base0 = a.base0, base1 = a.base1;                  // (L-2)*s, (L-3)*s from the host: see below
-    int toff0 = base0, toff1 = base1;                            // constant-bank matrix index of the two hottest climb steps
     const uint32_t* alias_leaf0 = AL + (size_t)d.mat_off[L] * q * q;
     const float* tt_leaf0 = TT + (size_t)d.mat_off[L] * Q * QS;
 
@@ -327,14 +319,12 @@ k_tree2(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a, co
         }
         // ---- (re)draw the ancestors at depths <= L-2 that changed (every s-th node at most) ----
         if (MODE == MODE_PHILOX && L > 2 && cj == 0) {
-            if (!FAST) {
-                int t2 = div_s<S>(j, d);                         // trailing zero base-s digits of j, capped at L-2
-                tz = 1;
-                while (tz < L - 2) {
-                    const int tq = div_s<S>(t2, d);
-                    if (t2 - tq * s != 0) break;
-                    t2 = tq; ++tz;
-                }
+            int t2 = div_s<S>(j, d);                             // trailing zero base-s digits of j, capped at L-2
+            tz = 1;
+            while (tz < L - 2) {
+                const int tq = div_s<S>(t2, d);
+                if (t2 - tq * s != 0) break;
+                t2 = tq; ++tz;
             }
             const int lstart = L - 1 - tz;                       // >= 1
             int xp[TPT];
@@ -342,13 +332,8 @@ k_tree2(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a, co
             for (int t = 0; t < TPT; ++t) xp[t] = VAL[((lstart - 1) * TPT + t) * NT + tid];
             for (int l = lstart; l <= L - 2; ++l) {
                 const int idx = ghm_div_pow(j, L - 1 - l, d);
-                int mi;
-                if (FAST) {
-                    mi = (l - 1) * s + (int)((D >> (4 * l)) & 15ull);
-                } else {
-                    const int c = idx - div_s<S>(idx, d) * s;
-                    mi = d.mat_off[l] + (d.ti ? c : idx);
-                }
+                const int c = idx - div_s<S>(idx, d) * s;
+                const int mi = d.mat_off[l] + (d.ti ? c : idx);
                 const uint32_t* arow = AL + (size_t)mi * q * q;
 #pragma unroll
                 for (int t = 0; t < TPT; ++t) {
@@ -370,7 +355,7 @@ k_tree2(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a, co
             for (int t = 0; t < TPT; ++t) xpar[t] = xp[t];
         }
         // ---- node j (depth L-1) and the s leaves under it -------------------------------------
-        const int mi_j = FAST ? (L - 2) * s + cj : d.mat_off[L > 1 ? L - 1 : 1] + (d.ti ? cj : j);   // matrix of the edge into node j
+        const int mi_j = d.mat_off[L > 1 ? L - 1 : 1] + (d.ti ? cj : j);   // matrix of the edge into node j
         uint4 rbL[TPT];
         if (MODE == MODE_PHILOX && L >= 2 && !spare) {           // s % 4 == 0: node j from the per-level block
 #pragma unroll
@@ -391,7 +376,7 @@ k_tree2(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a, co
 #pragma unroll
         for (int c = 0; c < s; ++c) {
             const int lidx = j * s + c;
-            const int moff = (FAST || d.ti) ? c : lidx;
+            const int moff = d.ti ? c : lidx;
             if (MODE == MODE_PHILOX && (c & 3) == 0) {
 #pragma unroll
                 for (int t = 0; t < TPT; ++t)
@@ -470,54 +455,18 @@ k_tree2(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a, co
                 }
                 return true;
             };
-            if (FAST) {
-                // The two hottest steps (every node / every s-th node) are peeled and read their table through the
-                // dedicated running offsets toff0 / toff1: values that feed nothing but the constant-bank address stay in
-                // UNIFORM registers (LDCU.64 + FFMA2 with a UR operand).  Sharing an index expression with the per-lane
-                // alias / row gathers would pull it into the vector datapath (per-thread LDC: measured 1.4x slower).
-                bool up = L >= 2;
-                if (up) up = climb_step(tab.v + toff0 * (Q * QS), toff0 != base0, toff0 == base0 + (s - 1), nullptr);
-                if (up && L >= 3)
-                    up = climb_step(tab.v + toff1 * (Q * QS), toff1 != base1, toff1 == base1 + (s - 1),
-                                    ACC + (size_t)(L - 3) * H * TPT * NT + tid);
-                if (up && L >= 4) {
-                    f2* A = ACC + (size_t)(L - 4) * H * TPT * NT + tid;
-                    for (int l = L - 3; l > 0; --l) {
-                        const int c = (int)((D >> (4 * l)) & 15ull);
-                        if (!climb_step(tab.v + ((l - 1) * s + c) * (Q * QS), c != 0, c == s - 1, A)) break;
-                        A -= H * TPT * NT;
-                    }
-                }
-            } else {
-                int idx = j;
-                for (int l = L - 1; l > 0; --l) {
-                    const int pidx = div_s<S>(idx, d);
-                    const int c = idx - pidx * s;
-                    const int mi = d.mat_off[l] + (d.ti ? c : idx);
-                    idx = pidx;
-                    f2* A = l == L - 1 ? nullptr : ACC + (size_t)(l - 1) * H * TPT * NT + tid;
-                    if (!climb_step(TT + (size_t)mi * Q * QS, c != 0, c == s - 1, A)) break;
-                }
+            int idx = j;
+            for (int l = L - 1; l > 0; --l) {
+                const int pidx = div_s<S>(idx, d);
+                const int c = idx - pidx * s;
+                const int mi = d.mat_off[l] + (d.ti ? c : idx);
+                idx = pidx;
+                f2* A = l == L - 1 ? nullptr : ACC + (size_t)(l - 1) * H * TPT * NT + tid;
+                if (!climb_step(TT + (size_t)mi * Q * QS, c != 0, c == s - 1, A)) break;
             }
         }
         // ---- advance the odometer ---------------------------------------------------------------
         if (++cj == s) cj = 0;
-        toff0 += 1;                                              // uniform-side twin of the odometer (table indices only)
-        if (toff0 == base0 + s) {
-            toff0 = base0;
-            toff1 += 1;
-            if (toff1 == base1 + s) toff1 = base1;
-        }
-        if (FAST) {
-            tz = 0;
-            for (int l = L - 1; l >= 1; --l) {
-                const int c = (int)((D >> (4 * l)) & 15ull) + 1;
-                if (c < s) { D += 1ull << (4 * l); break; }
-                D &= ~(15ull << (4 * l));
-                ++tz;
-            }
-            tz = min(tz, L > 2 ? L - 2 : 0);
-        }
         if (!FLAT && use_stage) {
             if (--chunk_left == 0 || j == n1 - 1) {
                 if (MODE == MODE_PHILOX) {
@@ -621,15 +570,20 @@ static int launch_tree2(const ghm_model* m, const TreeArgs& a0, bool want_smem_t
     }
 }
 
-// fast variants: s in {2,3,4}, T^T tables small enough for the constant-bank parameter, alias / leaf tables fit
-// in shared memory, whole rows staged (flat 16-byte streams); everything else (any s, per-edge tables too large,
-// n_L too large to stage whole rows, unaligned leaf pointer) takes the generic one-tree-per-thread variant.
-template <int Q, int S, int TPT, int MODE, bool BP>
+#include "ghm_tree_fast.cuh"
+
+// fast variant (k_tree_fast): translation-invariant tables, s in {2,3,4}, L >= 3, T^T tables small enough for the
+// constant-bank parameter, alias / leaf tables fit in shared memory, whole rows staged (flat 16-byte streams);
+// everything else (any s, shallow trees, per-edge tables, n_L too large to stage whole rows, unaligned leaf pointer)
+// takes the generic one-tree-per-thread instantiation of k_tree2 (S = 0, TPT = 1).
+template <int Q, int S, int MODE, bool BP>
 static int launch_fast(const ghm_model* m, const TreeArgs& a, cudaStream_t st) {
     constexpr int QS = (Q + 3) / 4 * 4;
-    if (!BP) return launch_tree2<Q, S, TPT, MODE, BP, true, 4>(m, a, true, st);
-    if ((size_t)m->d.n_mat * Q * QS <= 1536) return launch_tree2<Q, S, TPT, MODE, BP, true, 1536>(m, a, true, st);
-    return launch_tree2<Q, S, TPT, MODE, BP, true, 6144>(m, a, true, st);
+    if (!BP) return launch_tree_fast<Q, S, MODE, BP, 4>(m, a, st);
+    if constexpr (Q < 16) {                                        // small tables: a 6 KB parameter instead of 24 KB per launch
+        if ((size_t)m->d.n_mat * Q * QS <= 1536) return launch_tree_fast<Q, S, MODE, BP, 1536>(m, a, st);
+    }
+    return launch_tree_fast<Q, S, MODE, BP, 6144>(m, a, st);
 }
 
 template <int Q, int MODE, bool BP>
@@ -642,11 +596,11 @@ static int dispatch_variant(const ghm_model* m, const TreeArgs& a, cudaStream_t 
     if (MODE == MODE_PHILOX) smem_tab += ((size_t)d.n_mat * d.q * d.q * 4 + 15) / 16 * 16;
     const size_t flat_bytes = a.leaves ? ((size_t)64 * d.n_leaves + 15) / 16 * 16 * T2_WARPS : 0;
     const bool flat_ok = !a.leaves || (flat_bytes <= 48 * 1024 && ((uintptr_t)a.leaves % 16) == 0);
-    if (d.ti && ctab_words <= 6144 && smem_tab <= 40 * 1024 && flat_ok && d.s >= 2 && d.s <= 4) {
-        switch (d.s) {
-            case 2: return launch_fast<Q, 2, 2, MODE, BP>(m, a, st);
-            case 3: return launch_fast<Q, 3, 2, MODE, BP>(m, a, st);
-            default: return launch_fast<Q, 4, 2, MODE, BP>(m, a, st);
+    if (d.ti && d.L >= 3 && ctab_words <= 6144 && smem_tab <= 40 * 1024 && flat_ok && d.s >= 2 && d.s <= 4) {
+        switch (d.s) {                                             // software-pipelined variant (ghm_tree_fast.cuh)
+            case 2: return launch_fast<Q, 2, MODE, BP>(m, a, st);
+            case 3: return launch_fast<Q, 3, MODE, BP>(m, a, st);
+            default: return launch_fast<Q, 4, MODE, BP>(m, a, st);
         }
     }
     size_t gen_tab = 0;

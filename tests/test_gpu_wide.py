@@ -92,3 +92,66 @@ def test_wide_tcgen05_gemm_variants(ops, L, s, q, B, mode, tol):
     m.set_gemm_mode(m.GEMM_F32)
     p_again, _ = m.bp_cls(leaves)
     assert torch.equal(p_again, p32)
+
+
+# ---- 16 < q <= 256: next-token posteriors and the three guide sets (log-domain warp-per-row kernels) ----------
+def _cmp_list(got, ref, tag, atol=3e-5):
+    assert len(got) == len(ref), (tag, len(got), len(ref))
+    for i, (g, r) in enumerate(zip(got, ref)):
+        g = g.cpu().numpy()
+        assert g.shape == r.shape and g.dtype == np.float32, (tag, i, g.shape, r.shape)
+        fin = np.isfinite(r)
+        assert np.isfinite(g[fin]).all(), f"{tag} guide {i}: non-finite where the oracle is finite"
+        np.testing.assert_allclose(g[fin], r[fin], rtol=RTOL, atol=atol, err_msg=f"{tag} guide {i}")
+        assert (g[~fin] < -80).all(), f"{tag} guide {i}: entries the float64 oracle underflows must stay far below e^-80"
+
+
+@pytest.mark.parametrize("L,s,q,ti,B", [(3, 2, 20, True, 37), (2, 3, 64, True, 50), (3, 2, 100, False, 21), (2, 2, 256, True, 19)])
+def test_wide_bp_nwp_and_guides_vs_oracle(ops, L, s, q, ti, B):
+    """BP_NWP_autoregressive for q > 16 (reference :336-463): posteriors at 1e-5, every guide tensor (shifted
+    log-messages, :357-459) at 1e-5 relative + 3e-5 absolute against the float64 oracle, with and without ext."""
+    from oracle import ghm_oracle as O
+    T, py, m = _model(ops, L, s, q, ti, seed=11)
+    rng = np.random.RandomState(6)
+    vals = O.sample_tree(T, L, s, q, B, root=rng.randint(0, q, size=B), U=rng.rand(O.n_edges(L, s), B))
+    leaves = torch.from_numpy(vals[-1].T.copy()).cuda()
+    ext = np.log(rng.dirichlet(np.ones(q), size=B).T)
+    for e in (None, ext):
+        pp_ref, g_ref = O.bp_nwp(T, vals[-1], L, s, q, ext=e, guide=True)
+        et = None if e is None else torch.from_numpy(e.T.astype(np.float32)).cuda().contiguous()
+        pp = m.bp_nwp(leaves, et)
+        np.testing.assert_allclose(pp.cpu().numpy(), pp_ref, rtol=2e-5, atol=1e-7)
+        guides, pp2 = m.guides_nwp(leaves, et)
+        assert torch.equal(pp2, pp)
+        _cmp_list(guides, g_ref, "nwp")
+    pp8 = m.bp_nwp(leaves.to(torch.uint8), et)
+    assert torch.equal(pp8, pp)
+    assert m.status() == 0
+
+
+@pytest.mark.parametrize("L,s,q,ti,B,sigma", [(3, 2, 20, True, 33, 1.0), (2, 3, 64, True, 40, 0.5), (3, 2, 100, False, 17, 2.0),
+                                              (2, 2, 256, True, 12, 1.0)])
+def test_wide_guides_cls_dns_vs_oracle(ops, L, s, q, ti, B, sigma):
+    """guided_info for q > 16 (reference :526-592): cls set (hd per depth) and dns set ((hd|qd), root (hd|bu),
+    (hd|qd|bu)) against the float64 oracle; the posteriors they return equal the GEMM path's to 1e-5."""
+    from oracle import ghm_oracle as O
+    T, py, m = _model(ops, L, s, q, ti, seed=13)
+    rng = np.random.RandomState(8)
+    vals = O.sample_tree(T, L, s, q, B, root=rng.randint(0, q, size=B), U=rng.rand(O.n_edges(L, s), B))
+    leaves = torch.from_numpy(vals[-1].T.copy()).cuda()
+    post, hd = O.bp_cls(T, vals[-1], L, s, q, py)
+    guides, p, h = m.guides_cls(leaves)
+    np.testing.assert_allclose(p.cpu().numpy(), post.T, rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(h.cpu().numpy(), hd[0][0].T, rtol=RTOL, atol=2e-5)
+    _cmp_list(guides, O.guides_cls(hd, L, s), "cls")
+    z = vals[-1] + sigma * rng.randn(s ** L, B)
+    ext = hd[0][0]
+    zt = torch.from_numpy(z.T.astype(np.float32)).cuda().contiguous()
+    for e in (None, ext):
+        mean_ref, dhd, dqd, dbu = O.bp_dns(T, z, sigma, L, s, q, ext=e)
+        et = None if e is None else torch.from_numpy(e.T.astype(np.float32)).cuda().contiguous()
+        g, mean = m.guides_dns(zt, sigma, et)
+        np.testing.assert_allclose(mean.cpu().numpy(), mean_ref.T, rtol=2e-5, atol=2e-5 * q)
+        # leaf hd = -(z-k)^2 / 2 sigma^2 reaches -3e4 at q = 256: float32 resolution there is 2e-3, hence the relative bound
+        _cmp_list(g, O.guides_dns(dhd, dqd, dbu, L, s), "dns", atol=1e-4)
+    assert m.status() == 0

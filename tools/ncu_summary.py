@@ -1,6 +1,8 @@
 """Summarise one kernel of an .ncu-rep (ncu --set full ... -o file) as the small CSV kept under profiles/.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep "command that was profiled" > profiles/rNN_ncu_full_<kernel>.csv
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep "command that was profiled" [--index K] > profiles/rNN_ncu_full_<kernel>.csv
+
+--index K picks the K-th profiled launch of the report (default 0).
 
 Prints `metric,unit,value` rows for the launch configuration, time, DRAM traffic, pipe utilisation and issue
 statistics, then the instruction mix (top opcodes, share of executed warp instructions) and the warp-stall mix
@@ -34,8 +36,9 @@ def page(rep, name):
 def main():
     rep = sys.argv[1]
     what = sys.argv[2] if len(sys.argv) > 2 else ""
+    index = int(sys.argv[sys.argv.index("--index") + 1]) if "--index" in sys.argv else 0
     rows = page(rep, "raw")
-    hdr, units, val = rows[0], rows[1], rows[2]
+    hdr, units, val = rows[0], rows[1], rows[2 + index]
     print("# ncu --set full --clock-control none, one launch: %s" % what)
     print("metric,unit,value")
     print('Kernel Name,,"%s"' % val[hdr.index("Kernel Name")])
@@ -45,11 +48,16 @@ def main():
             print('%s,%s,"%s"' % (w, units[i], val[i]))
     src = page(rep, "source")
     h = None
+    sect = -1
     byop, stalls, total = collections.Counter(), collections.Counter(), 0
     for r in src:
         if len(r) > 3 and r[0] == "Address":
-            if h is not None:
+            sect += 1                                      # two "Address, Source, ..." sections per profiled launch
+            if sect > 2 * index:
                 break
+            if sect < 2 * index:
+                h = None
+                continue
             h = r
             i_src, i_exec = h.index("Source"), h.index("Instructions Executed")
             cols = [i for i, x in enumerate(h) if x.startswith("stall_") and "Not Issued" not in x]
