@@ -507,7 +507,8 @@ def strong_scaling(args, rank, world, dev, barrier):
             return s.get_Bayes(n_eval=n_pairs, distributed=distributed, lazy=True)
 
         def timed(distributed, reps):
-            evaluate(distributed).result()
+            for _ in range(2):                                # two warm evaluations: the caching allocator settles its blocks
+                evaluate(distributed).result()
             if distributed:
                 barrier()
             else:

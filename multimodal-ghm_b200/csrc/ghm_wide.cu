@@ -417,9 +417,13 @@ int ghm_wide_bp_dns(const ghm_model* m, int64_t B, const float* z, float sigma, 
         constexpr int NV = decltype(nvc)::value;
         int rc;
         // ---- upward ----
-        k_wide_leaf_like<NV><<<row_grid((int64_t)nL * B), WR_NT, 0, st>>>(d, B, z, c2, tA);
-        GHM_CHECK_LAUNCH();
-        if ((rc = ghm_wide_gemm(m, B, L, nL, 0, tA, Ud + off(L) * RW, st))) return rc;
+        rc = ghm_wide_leaf_up_fused(m, B, z, c2, Ud + off(L) * RW, st);      // TF32: likelihoods generated inside the GEMM
+        if (rc == GHM_EUNSUP) {
+            k_wide_leaf_like<NV><<<row_grid((int64_t)nL * B), WR_NT, 0, st>>>(d, B, z, c2, tA);
+            GHM_CHECK_LAUNCH();
+            rc = ghm_wide_gemm(m, B, L, nL, 0, tA, Ud + off(L) * RW, st);
+        }
+        if (rc) return rc;
         for (int l = L - 1; l >= 0; --l) {
             const int n = d.spow[l];
             k_wide_combine<NV><<<row_grid((int64_t)n * B), WR_NT, 0, st>>>(d, B, n, Ud + off(l + 1) * RW, Hd + off(l) * RW,
@@ -432,6 +436,10 @@ int ghm_wide_bp_dns(const ghm_model* m, int64_t B, const float* z, float sigma, 
         // ---- downward ----
         for (int l = 1; l <= L; ++l) {
             const int n = d.spow[l];
+            if (l == L) {                                     // TF32: cavity + GEMM + posterior mean in one kernel
+                rc = ghm_wide_leaf_down_fused(m, B, z, c2, BU + off(L - 1) * RW, Ud + off(L) * RW, mean, st);
+                if (rc != GHM_EUNSUP) return rc;
+            }
             k_wide_cavity<NV><<<row_grid((int64_t)n * B), WR_NT, 0, st>>>(d, B, n, BU + off(l - 1) * RW, Ud + off(l) * RW, tA);
             GHM_CHECK_LAUNCH();
             if ((rc = ghm_wide_gemm(m, B, l, n, 1, tA, tB, st))) return rc;

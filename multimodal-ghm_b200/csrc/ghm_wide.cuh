@@ -14,3 +14,9 @@ int ghm_wide_bp_dns(const ghm_model* m, int64_t B, const float* z, float sigma, 
 int ghm_wide_gemm(const ghm_model* m, int64_t B, int level, int n_nodes, int down, const float* X, float* Y, cudaStream_t st);
 // tcgen05 TF32 / BF16 variant (ghm_wide_tc.cu); returns GHM_EUNSUP for shapes it does not cover
 int ghm_wide_gemm_tc(const ghm_model* m, int64_t B, int level, int n_nodes, int down, const float* X, float* Y, cudaStream_t st);
+
+// BP_DNS leaf level with the likelihood / cavity / posterior-mean row kernels folded into the TF32 GEMM
+// (ghm_wide_tc.cu); GHM_EUNSUP when the model is not in TF32 mode or the shape is not covered
+int ghm_wide_leaf_up_fused(const ghm_model* m, int64_t B, const float* z, float c2, float* Uout, cudaStream_t st);
+int ghm_wide_leaf_down_fused(const ghm_model* m, int64_t B, const float* z, float c2, const float* BUpar, const float* U,
+                             float* mean, cudaStream_t st);

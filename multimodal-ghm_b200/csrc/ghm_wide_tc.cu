@@ -27,6 +27,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #define TC_THREADS 128
 #define TC_M 128
@@ -233,6 +234,44 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Epilogue of the warp-specialised kernels: TMEM -> registers (thread = row) -> a 32 x 32 transpose tile in shared memory
+// -> global with every store instruction covering four full 128-byte row segments.  Writing straight from the
+// thread-per-row registers made each STG.128 touch 32 different lines (16 bytes each at a 4N-byte stride): 8192
+// half-sector write transactions per 128 x 256 tile kept L1 busy 4 us per tile -- twice the MMA time (ncu: L1 52 %,
+// tensor pipe 22 %).
+#define EPI_PITCH 36                                           // floats per staged row: 16-byte aligned, conflict-free for LDS/STS.128
+__device__ __forceinline__ void epilogue_store_rows(uint32_t tmem_d, int quarter, int lane, int N, int64_t m0, int64_t B,
+                                                    float* __restrict__ Yn, float* __restrict__ stage) {
+    float* tile = stage + (size_t)quarter * 32 * EPI_PITCH;
+    const int64_t row0 = m0 + quarter * 32;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        __syncwarp();                                          // the previous chunk's reads of the tile are done
+        uint4* srow = reinterpret_cast<uint4*>(tile + (size_t)lane * EPI_PITCH);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) srow[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = (lane >> 3) + 4 * i;                // 4 rows x 128 bytes per instruction
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)rr * EPI_PITCH + 4 * (lane & 7));
+            if (row0 + rr < B) *reinterpret_cast<uint4*>(Yn + (row0 + rr) * N + c0 + 4 * (lane & 7)) = v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(TMA_THREADS) k_wide_gemm_tma(const __grid_constant__ CUtensorMap mapX,
                                                                const __grid_constant__ CUtensorMap mapW, const GhmDev d,
                                                                int64_t B, int level, int stages, float* __restrict__ Y) {
@@ -294,29 +333,306 @@ __global__ void __launch_bounds__(TMA_THREADS) k_wide_gemm_tma(const __grid_cons
         }
     } else {                                                  // ===== epilogue warps 2..5 =====
         const int quarter = warp & 3;                         // TMEM lane quarter this warp may access
+        mbar_wait(&tmem_full_bar, 0);                         // every MMA has completed: the operand stages are free
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        epilogue_store_rows(tmem_d, quarter, lane, N, m0, B, Y + (int64_t)node * B * N, reinterpret_cast<float*>(tiles));
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cluster variant: CL row tiles of ONE node form a thread-block cluster and share the weight operand.  What bounds
+// k_wide_gemm_tma is the L2 -> shared-memory traffic (profiles/r01_ncu_full_k_wide_gemm_tma.csv: L2 56 %, tensor pipe
+// 22 %): every 128-row tile pulls its own copy of the N x N weight (256 KB at N = 256) next to 128 KB of messages.
+// Here CTA r of the cluster loads rows [r N/CL, (r+1) N/CL) of each weight chunk and MULTICASTS them into the same
+// stage of all CL CTAs (cp.async.bulk.tensor ... .multicast::cluster), so a weight byte crosses L2 -> SM once per
+// cluster: (128 + 256 / CL) KB per tile instead of 384 KB.  A stage of a CTA is written by every CTA of the cluster,
+// so its EMPTY barrier counts CL arrivals: each CTA's tcgen05.commit arrives on that barrier in all CL CTAs
+// (.multicast::cluster).  Cluster barriers fence the mbarrier initialisation and the exit.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+        "[%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+
+template <int CL>
+__global__ void __launch_bounds__(TMA_THREADS) k_wide_gemm_tma_mc(const __grid_constant__ CUtensorMap mapX,
+                                                                  const __grid_constant__ CUtensorMap mapWs, const GhmDev d,
+                                                                  int64_t B, int level, int stages, float* __restrict__ Y) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = d.QW;
+    const int node = blockIdx.y;
+    const int64_t m0 = (int64_t)blockIdx.x * TC_M;
+    const int mi = d.mat_off[level] + (d.ti ? node - ghm_div_s(node, d) * d.s : node);
+    const uint32_t rank = cluster_ctarank();
+    const uint16_t mask = (uint16_t)((1u << CL) - 1u);
+    unsigned char* tiles = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = TC_M * 128, b_bytes = N * 128, stage_bytes = a_bytes + b_bytes;
+    const int slice_rows = N / CL, slice_bytes = slice_rows * 128;
+    const int nchunks = N / 32;
+    const uint32_t tmem_cols = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                       // every CTA's barriers are initialised before any peer signals them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                      // ===== TMA producer =====
+            for (int kc = 0; kc < nchunks; ++kc) {
+                const int st = kc % stages;
+                if (kc >= stages) mbar_wait(&empty_bar[st], ((kc / stages) - 1) & 1);   // all CL consumers released the stage
+                unsigned char* At = tiles + (size_t)st * stage_bytes;
+                mbar_expect_tx(&full_bar[st], (uint32_t)stage_bytes);
+                tma_load_2d(At, &mapX, &full_bar[st], kc * 32, (int)((int64_t)node * B + m0));
+                tma_load_2d_mc(At + a_bytes + (size_t)rank * slice_bytes, &mapWs, &full_bar[st], kc * 32,
+                               mi * N + (int)rank * slice_rows, mask);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                      // ===== MMA issuer =====
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            for (int kc = 0; kc < nchunks; ++kc) {
+                const int st = kc % stages;
+                mbar_wait(&full_bar[st], (kc / stages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                unsigned char* At = tiles + (size_t)st * stage_bytes;
+                const uint64_t adesc = umma_desc_sw128(smem_u32(At)), bdesc = umma_desc_sw128(smem_u32(At + a_bytes));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_issue<GHM_GEMM_TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
+                umma_commit_mc(&empty_bar[st], mask);         // this CTA is done with the stage: tell every producer of the cluster
+            }
+            umma_commit(&tmem_full_bar);                      // accumulator complete
+        }
+    } else {                                                  // ===== epilogue warps 2..5 =====
+        const int quarter = warp & 3;                         // TMEM lane quarter this warp may access
+        mbar_wait(&tmem_full_bar, 0);                         // every MMA has completed: the operand stages are free
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        epilogue_store_rows(tmem_d, quarter, lane, N, m0, B, Y + (int64_t)node * B * N, reinterpret_cast<float*>(tiles));
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                       // no CTA leaves while a peer may still signal its barriers
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Leaf-level GEMMs of BP_DNS with the row kernels folded in (TF32).  The per-launch ncu list of the unfused pass
+// (profiles/r02_launches_wide_dns.csv, q = 256, B = 16384) has the leaf level at 2.3 of 3.8 ms, more than half of it
+// in HBM-bound row kernels that only reshuffle GEMM operands:
+//   up   : k_wide_leaf_like writes the Gaussian likelihoods E (1.3 GB) that the GEMM reads straight back;
+//   down : k_wide_cavity writes w = b_parent / u (1.3 GB), the GEMM reads it and writes T^T w (1.3 GB), k_wide_belief
+//          reads that to form one float per leaf.
+// Here the A operand is COMPUTED into the swizzled shared-memory tile by the four epilogue warps (thread = tree row):
+//   LF_UP   : A[r][k] = exp2(c2 ((z_r - k)^2 - d0_r))  from one float per row   (reference :485)
+//   LF_DOWN : A[r][k] = b_parent[r][k] / u_leaf[r][k]                             (reference :513)
+// the weight still arrives by TMA, and the epilogue either stores u = T e (LF_UP, transposed to coalesced rows) or
+// reduces the posterior mean sum_k k e_k tt_k / sum_k e_k tt_k in registers (LF_DOWN, :516-519): nothing but the
+// inputs and the outputs of the level crosses HBM.
+// ------------------------------------------------------------------------------------------------
+enum { LF_UP = 0, LF_DOWN = 1 };
+struct LeafFusedArgs {
+    const float* z;          // [B][nL]
+    float c2;                // -0.5 log2(e) / sigma^2
+    const float* BUpar;      // [n_par][B][N]   (LF_DOWN) beliefs of the depth-(L-1) nodes
+    const float* U;          // [nL][B][N]      (LF_DOWN) upward leaf messages u = T e
+    float* Uout;             // [nL][B][N]      (LF_UP)
+    float* mean;             // [B][nL]         (LF_DOWN)
+};
+
+__device__ __forceinline__ float ex2_fast(float x) {          // arguments <= 0: MUFU.EX2, flushes to 0 far below 2^-126
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TMA_THREADS) k_wide_leaf_fused(const __grid_constant__ CUtensorMap mapW, const GhmDev d, int64_t B,
+                                                                 int stages, const LeafFusedArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = d.QW, q = d.q, nL = d.n_leaves;
+    const int node = blockIdx.y;                              // leaf index
+    const int64_t m0 = (int64_t)blockIdx.x * TC_M;
+    const int mi = d.mat_off[d.L] + (d.ti ? node - ghm_div_s(node, d) * d.s : node);
+    unsigned char* tiles = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = TC_M * 128, b_bytes = N * 128, stage_bytes = a_bytes + b_bytes;
+    const int nchunks = N / 32;
+    const uint32_t tmem_cols = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(&full_bar[i], 1 + 4); mbar_init(&empty_bar[i], 1); }   // TMA + 4 producer warps
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                      // ===== TMA producer: weight chunks =====
+            for (int kc = 0; kc < nchunks; ++kc) {
+                const int st = kc % stages;
+                if (kc >= stages) mbar_wait(&empty_bar[st], ((kc / stages) - 1) & 1);
+                unsigned char* At = tiles + (size_t)st * stage_bytes;
+                mbar_expect_tx(&full_bar[st], (uint32_t)b_bytes);
+                tma_load_2d(At + a_bytes, &mapW, &full_bar[st], kc * 32, mi * N);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                      // ===== MMA issuer =====
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            for (int kc = 0; kc < nchunks; ++kc) {
+                const int st = kc % stages;
+                mbar_wait(&full_bar[st], (kc / stages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                unsigned char* At = tiles + (size_t)st * stage_bytes;
+                const uint64_t adesc = umma_desc_sw128(smem_u32(At)), bdesc = umma_desc_sw128(smem_u32(At + a_bytes));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_issue<GHM_GEMM_TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
+                umma_commit(&empty_bar[st]);
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {                                                  // ===== warps 2..5: A producers, then epilogue =====
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;                    // tile row = TMEM lane
+        const int64_t b = m0 + r;
+        const bool ok = b < B;
+        float zi = 0.f, d0 = 0.f;
+        {
+            zi = ok ? a.z[b * nL + node] : 0.f;
+            const float kstar = fminf(fmaxf(rintf(zi), 0.f), (float)(q - 1));
+            d0 = (zi - kstar) * (zi - kstar);
+        }
+        // A production, coalesced: per instruction the warp covers 4 tile rows x 128 bytes -- lane -> (row rr = 4 i + lane / 8,
+        // 16-byte piece pc = lane % 8) -- and writes each piece straight to its SWIZZLE_128B slot (pc ^ (row & 7)).  (With
+        // thread = row every LDG.128 touched 32 different lines and L1 transactions, not HBM, set the pace.)
+        const int pc = lane & 7;
+        const int par = ghm_div_s(node, d);                   // depth-(L-1) parent of this leaf
+        for (int kc = 0; kc < nchunks; ++kc) {
+            const int st = kc % stages;
+            if (kc >= stages) mbar_wait(&empty_bar[st], ((kc / stages) - 1) & 1);
+            unsigned char* At = tiles + (size_t)st * stage_bytes;
+            float4 pbv[8], puv[8];
+            if (MODE == LF_DOWN) {                                       // all 16 loads of the chunk in flight before any use
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = quarter * 32 + 4 * i + (lane >> 3);
+                    const int64_t bc = min(m0 + rr, B - 1);              // rows past the batch re-read the last row; zeroed below
+                    pbv[i] = __ldg(reinterpret_cast<const float4*>(a.BUpar + ((int64_t)par * B + bc) * N + kc * 32) + pc);
+                    puv[i] = __ldg(reinterpret_cast<const float4*>(a.U + ((int64_t)node * B + bc) * N + kc * 32) + pc);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rl = 4 * i + (lane >> 3);                      // row within this warp's 32 rows
+                const int rr = quarter * 32 + rl;                        // tile row
+                const bool in = m0 + rr < B;
+                uint4 v;
+                if (MODE == LF_UP) {
+                    const float zr = __shfl_sync(0xffffffffu, zi, rl), dr = __shfl_sync(0xffffffffu, d0, rl);
+                    float e[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const int k = kc * 32 + 4 * pc + x;
+                        const float dk = zr - (float)k;
+                        e[x] = (in && k < q) ? ex2_fast(a.c2 * (dk * dk - dr)) : 0.f;
+                    }
+                    v = make_uint4(__float_as_uint(e[0]), __float_as_uint(e[1]), __float_as_uint(e[2]), __float_as_uint(e[3]));
+                } else {
+                    const float4 pb = pbv[i], pu = puv[i];
+                    v = make_uint4(__float_as_uint(in && pu.x > 0.f ? __fdividef(pb.x, pu.x) : 0.f),
+                                   __float_as_uint(in && pu.y > 0.f ? __fdividef(pb.y, pu.y) : 0.f),
+                                   __float_as_uint(in && pu.z > 0.f ? __fdividef(pb.z, pu.z) : 0.f),
+                                   __float_as_uint(in && pu.w > 0.f ? __fdividef(pb.w, pu.w) : 0.f));
+                }
+                *reinterpret_cast<uint4*>(At + (size_t)rr * 128 + ((pc ^ (rr & 7)) << 4)) = v;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> async proxy (UMMA)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[st]);
+        }
         mbar_wait(&tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int64_t row = m0 + quarter * 32 + lane;
-        float* Yn = Y + (int64_t)node * B * N;
-        for (int c0 = 0; c0 < N; c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < B) {
-                uint4* dst = reinterpret_cast<uint4*>(Yn + row * N + c0);
+        if (MODE == LF_UP) {
+            epilogue_store_rows(tmem_d, quarter, lane, N, m0, B, a.Uout + (int64_t)node * B * N, reinterpret_cast<float*>(tiles));
+        } else {
+            float num = 0.f, den = 0.f;
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                uint32_t t[32];
+                const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]),
+                      "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15]), "=r"(t[16]),
+                      "=r"(t[17]), "=r"(t[18]), "=r"(t[19]), "=r"(t[20]), "=r"(t[21]), "=r"(t[22]), "=r"(t[23]), "=r"(t[24]),
+                      "=r"(t[25]), "=r"(t[26]), "=r"(t[27]), "=r"(t[28]), "=r"(t[29]), "=r"(t[30]), "=r"(t[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dst[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                for (int j = 0; j < 32; ++j) {
+                    const int k = c0 + j;
+                    const float dk = zi - (float)k;
+                    const float bl = k < q ? ex2_fast(a.c2 * (dk * dk - d0)) * __uint_as_float(t[j]) : 0.f;
+                    num = fmaf((float)k, bl, num);
+                    den += bl;
+                }
             }
+            if (ok) a.mean[b * nL + node] = num / den;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -372,8 +688,33 @@ static int launch_gemm_tma(const ghm_model* m, int64_t B, int level, int n_nodes
     int stages = std::min(4, nchunks);
     while (stages > 2 && (size_t)stages * stage_bytes + 1024 > 110 * 1024) --stages;     // two CTAs per SM
     const size_t dyn = (size_t)stages * stage_bytes + 1024;
+    const unsigned tiles = (unsigned)((B + TC_M - 1) / TC_M);
+    // cluster of CL row tiles sharing the multicast weight operand (GHM_WIDE_CLUSTER=1 keeps the single-CTA kernel)
+    static const int cl_env = getenv("GHM_WIDE_CLUSTER") ? atoi(getenv("GHM_WIDE_CLUSTER")) : 1;
+    int CL = tiles >= 4 && cl_env >= 4 ? 4 : (tiles >= 2 && cl_env >= 2 ? 2 : 1);
+    if (CL > 1) {
+        CUtensorMap mapWs;
+        if (!make_map(&mapWs, down ? d.Wdn : d.Wup, (uint64_t)d.n_mat * (uint64_t)N, N, N / CL)) return GHM_EUNSUP;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((tiles + CL - 1) / CL * CL, (unsigned)n_nodes, 1);
+        cfg.blockDim = dim3(TMA_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = dyn;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (CL == 4) {
+            GHM_CUDA_TRY(cudaFuncSetAttribute(k_wide_gemm_tma_mc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            GHM_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_wide_gemm_tma_mc<4>, mapX, mapWs, d, B, level, stages, Y));
+        } else {
+            GHM_CUDA_TRY(cudaFuncSetAttribute(k_wide_gemm_tma_mc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            GHM_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_wide_gemm_tma_mc<2>, mapX, mapWs, d, B, level, stages, Y));
+        }
+        return GHM_OK;
+    }
     GHM_CUDA_TRY(cudaFuncSetAttribute(k_wide_gemm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    dim3 grid((unsigned)((B + TC_M - 1) / TC_M), (unsigned)n_nodes);
+    dim3 grid(tiles, (unsigned)n_nodes);
     k_wide_gemm_tma<<<grid, TMA_THREADS, dyn, st>>>(mapX, mapW, d, B, level, stages, Y);
     GHM_CHECK_LAUNCH();
     return GHM_OK;
@@ -407,4 +748,47 @@ int ghm_wide_gemm_tc(const ghm_model* m, int64_t B, int level, int n_nodes, int 
     }
     GHM_CHECK_LAUNCH();
     return GHM_OK;
+}
+
+
+// Leaf level of BP_DNS with the row kernels folded into the TF32 GEMM (see k_wide_leaf_fused).  GHM_EUNSUP when the
+// shape / mode / driver does not allow it: the caller runs the unfused kernels.
+static int launch_leaf_fused(const ghm_model* m, int64_t B, int mode, const LeafFusedArgs& a, cudaStream_t st) {
+    const GhmDev& d = m->d;
+    const int N = d.QW;
+    if (m->gemm_mode != GHM_GEMM_TF32) return GHM_EUNSUP;
+    if (const char* e = getenv("GHM_WIDE_UNFUSED")) {          // development switch: "1" = both levels, "up" / "down" = one
+        if (e[0] == '1' || (e[0] == 'u' && mode == LF_UP) || (e[0] == 'd' && mode == LF_DOWN)) return GHM_EUNSUP;
+    }
+    if (N != 64 && N != 128 && N != 192 && N != 256) return GHM_EUNSUP;
+    if (d.n_leaves > 65535) return GHM_EUNSUP;
+    CUtensorMap mapW;
+    if (!make_map(&mapW, mode == LF_DOWN ? d.Wdn : d.Wup, (uint64_t)d.n_mat * (uint64_t)N, N, N)) return GHM_EUNSUP;
+    const int stage_bytes = TC_M * 128 + N * 128;
+    int stages = std::min(4, N / 32);
+    while (stages > 2 && (size_t)stages * stage_bytes + 1024 > 110 * 1024) --stages;     // two CTAs per SM
+    const size_t dyn = (size_t)stages * stage_bytes + 1024;
+    dim3 grid((unsigned)((B + TC_M - 1) / TC_M), (unsigned)d.n_leaves);
+    if (mode == LF_UP) {
+        GHM_CUDA_TRY(cudaFuncSetAttribute(k_wide_leaf_fused<LF_UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        k_wide_leaf_fused<LF_UP><<<grid, TMA_THREADS, dyn, st>>>(mapW, d, B, stages, a);
+    } else {
+        GHM_CUDA_TRY(cudaFuncSetAttribute(k_wide_leaf_fused<LF_DOWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        k_wide_leaf_fused<LF_DOWN><<<grid, TMA_THREADS, dyn, st>>>(mapW, d, B, stages, a);
+    }
+    GHM_CHECK_LAUNCH();
+    return GHM_OK;
+}
+
+int ghm_wide_leaf_up_fused(const ghm_model* m, int64_t B, const float* z, float c2, float* Uout, cudaStream_t st) {
+    LeafFusedArgs a{};
+    a.z = z; a.c2 = c2; a.Uout = Uout;
+    return launch_leaf_fused(m, B, LF_UP, a, st);
+}
+
+int ghm_wide_leaf_down_fused(const ghm_model* m, int64_t B, const float* z, float c2, const float* BUpar, const float* U,
+                             float* mean, cudaStream_t st) {
+    LeafFusedArgs a{};
+    a.z = z; a.c2 = c2; a.BUpar = BUpar; a.U = U; a.mean = mean;
+    return launch_leaf_fused(m, B, LF_DOWN, a, st);
 }
