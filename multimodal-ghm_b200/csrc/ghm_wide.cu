@@ -439,6 +439,10 @@ int ghm_wide_bp_dns(const ghm_model* m, int64_t B, const float* z, float sigma, 
             if (l == L) {                                     // TF32: cavity + GEMM + posterior mean in one kernel
                 rc = ghm_wide_leaf_down_fused(m, B, z, c2, BU + off(L - 1) * RW, Ud + off(L) * RW, mean, st);
                 if (rc != GHM_EUNSUP) return rc;
+            } else {                                          // TF32: cavity + GEMM + belief in one kernel
+                rc = ghm_wide_down_fused(m, B, l, BU + off(l - 1) * RW, Ud + off(l) * RW, Hd + off(l) * RW, BU + off(l) * RW, st);
+                if (rc == GHM_OK) continue;
+                if (rc != GHM_EUNSUP) return rc;
             }
             k_wide_cavity<NV><<<row_grid((int64_t)n * B), WR_NT, 0, st>>>(d, B, n, BU + off(l - 1) * RW, Ud + off(l) * RW, tA);
             GHM_CHECK_LAUNCH();

@@ -20,3 +20,6 @@ int ghm_wide_gemm_tc(const ghm_model* m, int64_t B, int level, int n_nodes, int 
 int ghm_wide_leaf_up_fused(const ghm_model* m, int64_t B, const float* z, float c2, float* Uout, cudaStream_t st);
 int ghm_wide_leaf_down_fused(const ghm_model* m, int64_t B, const float* z, float c2, const float* BUpar, const float* U,
                              float* mean, cudaStream_t st);
+// internal level l of the downward pass: beliefs BU[l] = hd * (T^T (BU[l-1] / u)) / max in one kernel
+int ghm_wide_down_fused(const ghm_model* m, int64_t B, int level, const float* BUpar, const float* U, const float* H, float* BU,
+                        cudaStream_t st);

@@ -240,35 +240,76 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // half-sector write transactions per 128 x 256 tile kept L1 busy 4 us per tile -- twice the MMA time (ncu: L1 52 %,
 // tensor pipe 22 %).
 #define EPI_PITCH 36                                           // floats per staged row: 16-byte aligned, conflict-free for LDS/STS.128
+// 32 consecutive TMEM columns of this thread's lane (= tile row) <-> 32 registers
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// one 32-row x 32-column block: registers (thread = row) -> transpose tile -> global, 4 rows x 128 bytes per store
+__device__ __forceinline__ void tile_store_block(float* tile, int lane, const uint32_t (&r)[32], float scale, float* __restrict__ Yn,
+                                                 int N, int64_t row0, int64_t B, int c0) {
+    __syncwarp();                                              // earlier reads of the tile are done
+    uint4* srow = reinterpret_cast<uint4*>(tile + (size_t)lane * EPI_PITCH);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        srow[j] = make_uint4(__float_as_uint(__uint_as_float(r[4 * j]) * scale), __float_as_uint(__uint_as_float(r[4 * j + 1]) * scale),
+                             __float_as_uint(__uint_as_float(r[4 * j + 2]) * scale), __float_as_uint(__uint_as_float(r[4 * j + 3]) * scale));
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = (lane >> 3) + 4 * i;
+        const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)rr * EPI_PITCH + 4 * (lane & 7));
+        if (row0 + rr < B) *reinterpret_cast<uint4*>(Yn + (row0 + rr) * N + c0 + 4 * (lane & 7)) = v;
+    }
+}
+// the reverse: global block (coalesced) -> transpose tile -> 32 registers of this thread's row
+__device__ __forceinline__ void tile_load_block(float* tile, int lane, float (&h)[32], const float* __restrict__ Xn, int N, int64_t row0,
+                                                int64_t B, int c0) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = (lane >> 3) + 4 * i;
+        const int64_t rc = min(row0 + rr, B - 1);
+        *reinterpret_cast<uint4*>(tile + (size_t)rr * EPI_PITCH + 4 * (lane & 7)) =
+            __ldg(reinterpret_cast<const uint4*>(Xn + rc * N + c0 + 4 * (lane & 7)));
+    }
+    __syncwarp();
+    const float4* srow = reinterpret_cast<const float4*>(tile + (size_t)lane * EPI_PITCH);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float4 v = srow[j]; h[4 * j] = v.x; h[4 * j + 1] = v.y; h[4 * j + 2] = v.z; h[4 * j + 3] = v.w; }
+}
+
+// columns c_first, c_first + c_stride, ... of this warp's TMEM lane quarter -> global rows (tile_id picks the transpose tile)
 __device__ __forceinline__ void epilogue_store_rows(uint32_t tmem_d, int quarter, int lane, int N, int64_t m0, int64_t B,
-                                                    float* __restrict__ Yn, float* __restrict__ stage) {
-    float* tile = stage + (size_t)quarter * 32 * EPI_PITCH;
+                                                    float* __restrict__ Yn, float* __restrict__ stage, int tile_id = -1,
+                                                    int c_first = 0, int c_stride = 32) {
+    float* tile = stage + (size_t)(tile_id < 0 ? quarter : tile_id) * 32 * EPI_PITCH;
     const int64_t row0 = m0 + quarter * 32;
-    for (int c0 = 0; c0 < N; c0 += 32) {
+    for (int c0 = c_first; c0 < N; c0 += c_stride) {
         uint32_t r[32];
-        const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        __syncwarp();                                          // the previous chunk's reads of the tile are done
-        uint4* srow = reinterpret_cast<uint4*>(tile + (size_t)lane * EPI_PITCH);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) srow[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int rr = (lane >> 3) + 4 * i;                // 4 rows x 128 bytes per instruction
-            const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)rr * EPI_PITCH + 4 * (lane & 7));
-            if (row0 + rr < B) *reinterpret_cast<uint4*>(Yn + (row0 + rr) * N + c0 + 4 * (lane & 7)) = v;
-        }
+        tmem_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        tile_store_block(tile, lane, r, 1.0f, Yn, N, row0, B, c0);
     }
 }
 
@@ -454,27 +495,35 @@ __global__ void __launch_bounds__(TMA_THREADS) k_wide_gemm_tma_mc(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
-// Leaf-level GEMMs of BP_DNS with the row kernels folded in (TF32).  The per-launch ncu list of the unfused pass
-// (profiles/r02_launches_wide_dns.csv, q = 256, B = 16384) has the leaf level at 2.3 of 3.8 ms, more than half of it
-// in HBM-bound row kernels that only reshuffle GEMM operands:
-//   up   : k_wide_leaf_like writes the Gaussian likelihoods E (1.3 GB) that the GEMM reads straight back;
-//   down : k_wide_cavity writes w = b_parent / u (1.3 GB), the GEMM reads it and writes T^T w (1.3 GB), k_wide_belief
-//          reads that to form one float per leaf.
-// Here the A operand is COMPUTED into the swizzled shared-memory tile by the four epilogue warps (thread = tree row):
-//   LF_UP   : A[r][k] = exp2(c2 ((z_r - k)^2 - d0_r))  from one float per row   (reference :485)
-//   LF_DOWN : A[r][k] = b_parent[r][k] / u_leaf[r][k]                             (reference :513)
-// the weight still arrives by TMA, and the epilogue either stores u = T e (LF_UP, transposed to coalesced rows) or
-// reduces the posterior mean sum_k k e_k tt_k / sum_k e_k tt_k in registers (LF_DOWN, :516-519): nothing but the
-// inputs and the outputs of the level crosses HBM.
+// BP_DNS GEMMs with the row kernels folded in (TF32).  The per-launch ncu list of the unfused pass
+// (profiles/r02_launches_wide_dns_unfused.csv, q = 256, B = 16384) spends 2.1 of 3.8 ms in HBM-bound row kernels that only
+// reshuffle GEMM operands:
+//   leaves, up   : k_wide_leaf_like writes the Gaussian likelihoods E (1.3 GB) that the GEMM reads straight back;
+//   every level, down : k_wide_cavity writes w = b_parent / u, the GEMM reads it and writes T^T w, k_wide_belief reads that
+//                       (and hd) to form the belief -- or, at the leaves, one float per row.
+// Here the A operand is COMPUTED into the swizzled shared-memory tile by eight producer warps (coalesced: per instruction
+// a warp covers 4 tile rows x 128 bytes and writes each 16-byte piece to its SWIZZLE_128B slot):
+//   LF_UP       : A[r][k] = exp2(c2 ((z_r - k)^2 - d0_r))  from one float per row   (reference :485)
+//   LF_DOWN(_INT): A[r][k] = b_parent[r][k] / u_v[r][k]                              (reference :513)
+// the weight still arrives by TMA, and the same eight warps run the epilogue on the TMEM accumulator:
+//   LF_UP       : store u = T e (transposed to coalesced rows);
+//   LF_DOWN     : posterior mean sum_k k e_k tt_k / sum_k e_k tt_k reduced in registers (:516-519);
+//   LF_DOWN_INT : belief b_v = hd_v * tt / max (:512-514): product written back to TMEM, row max exchanged between the
+//                 two warps of a lane quarter, second pass rescales and stores.
+// Nothing but the inputs and the outputs of a level crosses HBM.
 // ------------------------------------------------------------------------------------------------
-enum { LF_UP = 0, LF_DOWN = 1 };
-struct LeafFusedArgs {
-    const float* z;          // [B][nL]
+enum { LF_UP = 0, LF_DOWN = 1, LF_DOWN_INT = 2 };
+#define FUSED_PROD_WARPS 8
+#define FUSED_THREADS (64 + 32 * FUSED_PROD_WARPS)
+struct FusedArgs {
+    int level;               // depth of the nodes this launch covers (blockIdx.y = node index within the level)
+    const float* z;          // [B][nL]                     (leaf modes)
     float c2;                // -0.5 log2(e) / sigma^2
-    const float* BUpar;      // [n_par][B][N]   (LF_DOWN) beliefs of the depth-(L-1) nodes
-    const float* U;          // [nL][B][N]      (LF_DOWN) upward leaf messages u = T e
-    float* Uout;             // [nL][B][N]      (LF_UP)
-    float* mean;             // [B][nL]         (LF_DOWN)
+    const float* BUpar;      // [n_par][B][N] beliefs of the parents          (LF_DOWN, LF_DOWN_INT)
+    const float* U;          // [n][B][N]     upward messages u = T h         (LF_DOWN, LF_DOWN_INT)
+    const float* H;          // [n][B][N]     hd of the nodes                 (LF_DOWN_INT)
+    float* out;              // [n][B][N]     LF_UP: u;  LF_DOWN_INT: beliefs
+    float* mean;             // [B][nL]       (LF_DOWN)
 };
 
 __device__ __forceinline__ float ex2_fast(float x) {          // arguments <= 0: MUFU.EX2, flushes to 0 far below 2^-126
@@ -485,25 +534,29 @@ __device__ __forceinline__ float ex2_fast(float x) {          // arguments <= 0:
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void producers_sync() {            // named barrier 1: the eight producer / epilogue warps only
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * FUSED_PROD_WARPS) : "memory");
+}
 
 template <int MODE>
-__global__ void __launch_bounds__(TMA_THREADS) k_wide_leaf_fused(const __grid_constant__ CUtensorMap mapW, const GhmDev d, int64_t B,
-                                                                 int stages, const LeafFusedArgs a) {
+__global__ void __launch_bounds__(FUSED_THREADS) k_wide_fused(const __grid_constant__ CUtensorMap mapW, const GhmDev d, int64_t B,
+                                                              int stages, const FusedArgs a) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float2 red[TC_M];                              // per-row exchange between the two warps of a lane quarter
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = d.QW, q = d.q, nL = d.n_leaves;
-    const int node = blockIdx.y;                              // leaf index
+    const int node = blockIdx.y;
     const int64_t m0 = (int64_t)blockIdx.x * TC_M;
-    const int mi = d.mat_off[d.L] + (d.ti ? node - ghm_div_s(node, d) * d.s : node);
+    const int mi = d.mat_off[a.level] + (d.ti ? node - ghm_div_s(node, d) * d.s : node);
     unsigned char* tiles = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int a_bytes = TC_M * 128, b_bytes = N * 128, stage_bytes = a_bytes + b_bytes;
     const int nchunks = N / 32;
     const uint32_t tmem_cols = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(&full_bar[i], 1 + 4); mbar_init(&empty_bar[i], 1); }   // TMA + 4 producer warps
+        for (int i = 0; i < 4; ++i) { mbar_init(&full_bar[i], 1 + FUSED_PROD_WARPS); mbar_init(&empty_bar[i], 1); }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -544,39 +597,38 @@ __global__ void __launch_bounds__(TMA_THREADS) k_wide_leaf_fused(const __grid_co
             }
             umma_commit(&tmem_full_bar);
         }
-    } else {                                                  // ===== warps 2..5: A producers, then epilogue =====
-        const int quarter = warp & 3;
-        const int r = quarter * 32 + lane;                    // tile row = TMEM lane
+    } else {                                                  // ===== warps 2..9: A producers, then epilogue =====
+        const int quarter = warp & 3;                         // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                     // two warps share a quarter: rows 16 half .. +15 / alternate column blocks
+        const int pid = warp - 2;
+        const int r = quarter * 32 + lane;                    // tile row owned in the thread = row phases
         const int64_t b = m0 + r;
         const bool ok = b < B;
         float zi = 0.f, d0 = 0.f;
-        {
+        if (MODE != LF_DOWN_INT) {
             zi = ok ? a.z[b * nL + node] : 0.f;
             const float kstar = fminf(fmaxf(rintf(zi), 0.f), (float)(q - 1));
             d0 = (zi - kstar) * (zi - kstar);
         }
-        // A production, coalesced: per instruction the warp covers 4 tile rows x 128 bytes -- lane -> (row rr = 4 i + lane / 8,
-        // 16-byte piece pc = lane % 8) -- and writes each piece straight to its SWIZZLE_128B slot (pc ^ (row & 7)).  (With
-        // thread = row every LDG.128 touched 32 different lines and L1 transactions, not HBM, set the pace.)
         const int pc = lane & 7;
-        const int par = ghm_div_s(node, d);                   // depth-(L-1) parent of this leaf
+        const int par = ghm_div_s(node, d);
         for (int kc = 0; kc < nchunks; ++kc) {
             const int st = kc % stages;
             if (kc >= stages) mbar_wait(&empty_bar[st], ((kc / stages) - 1) & 1);
             unsigned char* At = tiles + (size_t)st * stage_bytes;
-            float4 pbv[8], puv[8];
-            if (MODE == LF_DOWN) {                                       // all 16 loads of the chunk in flight before any use
+            float4 pbv[4], puv[4];
+            if (MODE != LF_UP) {                                         // all 8 loads of the chunk in flight before any use
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rr = quarter * 32 + 4 * i + (lane >> 3);
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = quarter * 32 + 16 * half + 4 * i + (lane >> 3);
                     const int64_t bc = min(m0 + rr, B - 1);              // rows past the batch re-read the last row; zeroed below
                     pbv[i] = __ldg(reinterpret_cast<const float4*>(a.BUpar + ((int64_t)par * B + bc) * N + kc * 32) + pc);
                     puv[i] = __ldg(reinterpret_cast<const float4*>(a.U + ((int64_t)node * B + bc) * N + kc * 32) + pc);
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int rl = 4 * i + (lane >> 3);                      // row within this warp's 32 rows
+            for (int i = 0; i < 4; ++i) {
+                const int rl = 16 * half + 4 * i + (lane >> 3);          // row within the quarter
                 const int rr = quarter * 32 + rl;                        // tile row
                 const bool in = m0 + rr < B;
                 uint4 v;
@@ -603,26 +655,17 @@ __global__ void __launch_bounds__(TMA_THREADS) k_wide_leaf_fused(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[st]);
         }
-        mbar_wait(&tmem_full_bar, 0);
+        mbar_wait(&tmem_full_bar, 0);                         // every MMA has completed: the operand stages are free
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* stage_f = reinterpret_cast<float*>(tiles);
+        const uint32_t tlane = tmem_d + ((uint32_t)(quarter * 32) << 16);
         if (MODE == LF_UP) {
-            epilogue_store_rows(tmem_d, quarter, lane, N, m0, B, a.Uout + (int64_t)node * B * N, reinterpret_cast<float*>(tiles));
-        } else {
+            epilogue_store_rows(tmem_d, quarter, lane, N, m0, B, a.out + (int64_t)node * B * N, stage_f, pid, 32 * half, 64);
+        } else if (MODE == LF_DOWN) {
             float num = 0.f, den = 0.f;
-            for (int c0 = 0; c0 < N; c0 += 32) {
+            for (int c0 = 32 * half; c0 < N; c0 += 64) {
                 uint32_t t[32];
-                const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]),
-                      "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15]), "=r"(t[16]),
-                      "=r"(t[17]), "=r"(t[18]), "=r"(t[19]), "=r"(t[20]), "=r"(t[21]), "=r"(t[22]), "=r"(t[23]), "=r"(t[24]),
-                      "=r"(t[25]), "=r"(t[26]), "=r"(t[27]), "=r"(t[28]), "=r"(t[29]), "=r"(t[30]), "=r"(t[31])
-                    : "r"(taddr)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_ld32(tlane + (uint32_t)c0, t);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int k = c0 + j;
@@ -632,7 +675,42 @@ __global__ void __launch_bounds__(TMA_THREADS) k_wide_leaf_fused(const __grid_co
                     den += bl;
                 }
             }
-            if (ok) a.mean[b * nL + node] = num / den;
+            if (half == 1) red[r] = make_float2(num, den);
+            producers_sync();
+            if (half == 0 && ok) {
+                const float2 o = red[r];
+                a.mean[b * nL + node] = (num + o.x) / (den + o.y);
+            }
+        } else {
+            // pass 1: product hd * tt back into TMEM, row max over this warp's column blocks
+            float* tile = stage_f + (size_t)pid * 32 * EPI_PITCH;
+            const float* Hn = a.H + (int64_t)node * B * N;
+            const int64_t row0 = m0 + quarter * 32;
+            float mx = 0.f;
+            for (int c0 = 32 * half; c0 < N; c0 += 64) {
+                uint32_t t[32];
+                float h[32];
+                tmem_ld32(tlane + (uint32_t)c0, t);
+                tile_load_block(tile, lane, h, Hn, N, row0, B, c0);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float p = h[j] * __uint_as_float(t[j]);
+                    mx = fmaxf(mx, p);
+                    t[j] = __float_as_uint(p);
+                }
+                tmem_st32(tlane + (uint32_t)c0, t);
+            }
+            if (half == 1) red[r].y = mx; else red[r].x = mx;  // the two warps of a quarter own the same rows
+            producers_sync();
+            const float2 both = red[r];
+            const float inv = __fdividef(1.f, fmaxf(both.x, both.y));
+            // pass 2: rescale and store
+            float* BUn = a.out + (int64_t)node * B * N;
+            for (int c0 = 32 * half; c0 < N; c0 += 64) {
+                uint32_t t[32];
+                tmem_ld32(tlane + (uint32_t)c0, t);
+                tile_store_block(tile, lane, t, inv, BUn, N, row0, B, c0);
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -751,44 +829,52 @@ int ghm_wide_gemm_tc(const ghm_model* m, int64_t B, int level, int n_nodes, int 
 }
 
 
-// Leaf level of BP_DNS with the row kernels folded into the TF32 GEMM (see k_wide_leaf_fused).  GHM_EUNSUP when the
-// shape / mode / driver does not allow it: the caller runs the unfused kernels.
-static int launch_leaf_fused(const ghm_model* m, int64_t B, int mode, const LeafFusedArgs& a, cudaStream_t st) {
+// BP_DNS levels with the row kernels folded into the TF32 GEMM (see k_wide_fused).  GHM_EUNSUP when the shape / mode /
+// driver does not allow it: the caller runs the unfused kernels.
+static int launch_fused(const ghm_model* m, int64_t B, int mode, int n_nodes, const FusedArgs& a, cudaStream_t st) {
     const GhmDev& d = m->d;
     const int N = d.QW;
     if (m->gemm_mode != GHM_GEMM_TF32) return GHM_EUNSUP;
-    if (const char* e = getenv("GHM_WIDE_UNFUSED")) {          // development switch: "1" = both levels, "up" / "down" = one
-        if (e[0] == '1' || (e[0] == 'u' && mode == LF_UP) || (e[0] == 'd' && mode == LF_DOWN)) return GHM_EUNSUP;
+    if (const char* e = getenv("GHM_WIDE_UNFUSED")) {          // development switch: "1" = all, "up" / "down" / "int" = one mode
+        if (e[0] == '1' || (e[0] == 'u' && mode == LF_UP) || (e[0] == 'd' && mode == LF_DOWN) || (e[0] == 'i' && mode == LF_DOWN_INT))
+            return GHM_EUNSUP;
     }
     if (N != 64 && N != 128 && N != 192 && N != 256) return GHM_EUNSUP;
-    if (d.n_leaves > 65535) return GHM_EUNSUP;
+    if (n_nodes > 65535) return GHM_EUNSUP;
     CUtensorMap mapW;
-    if (!make_map(&mapW, mode == LF_DOWN ? d.Wdn : d.Wup, (uint64_t)d.n_mat * (uint64_t)N, N, N)) return GHM_EUNSUP;
+    if (!make_map(&mapW, mode == LF_UP ? d.Wup : d.Wdn, (uint64_t)d.n_mat * (uint64_t)N, N, N)) return GHM_EUNSUP;
     const int stage_bytes = TC_M * 128 + N * 128;
     int stages = std::min(4, N / 32);
     while (stages > 2 && (size_t)stages * stage_bytes + 1024 > 110 * 1024) --stages;     // two CTAs per SM
     const size_t dyn = (size_t)stages * stage_bytes + 1024;
-    dim3 grid((unsigned)((B + TC_M - 1) / TC_M), (unsigned)d.n_leaves);
-    if (mode == LF_UP) {
-        GHM_CUDA_TRY(cudaFuncSetAttribute(k_wide_leaf_fused<LF_UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        k_wide_leaf_fused<LF_UP><<<grid, TMA_THREADS, dyn, st>>>(mapW, d, B, stages, a);
-    } else {
-        GHM_CUDA_TRY(cudaFuncSetAttribute(k_wide_leaf_fused<LF_DOWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        k_wide_leaf_fused<LF_DOWN><<<grid, TMA_THREADS, dyn, st>>>(mapW, d, B, stages, a);
-    }
-    GHM_CHECK_LAUNCH();
-    return GHM_OK;
+    dim3 grid((unsigned)((B + TC_M - 1) / TC_M), (unsigned)n_nodes);
+    auto go = [&](auto kern) -> int {
+        GHM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        kern<<<grid, FUSED_THREADS, dyn, st>>>(mapW, d, B, stages, a);
+        GHM_CHECK_LAUNCH();
+        return GHM_OK;
+    };
+    if (mode == LF_UP) return go(k_wide_fused<LF_UP>);
+    if (mode == LF_DOWN) return go(k_wide_fused<LF_DOWN>);
+    return go(k_wide_fused<LF_DOWN_INT>);
 }
 
 int ghm_wide_leaf_up_fused(const ghm_model* m, int64_t B, const float* z, float c2, float* Uout, cudaStream_t st) {
-    LeafFusedArgs a{};
-    a.z = z; a.c2 = c2; a.Uout = Uout;
-    return launch_leaf_fused(m, B, LF_UP, a, st);
+    FusedArgs a{};
+    a.level = m->d.L; a.z = z; a.c2 = c2; a.out = Uout;
+    return launch_fused(m, B, LF_UP, m->d.n_leaves, a, st);
 }
 
 int ghm_wide_leaf_down_fused(const ghm_model* m, int64_t B, const float* z, float c2, const float* BUpar, const float* U,
                              float* mean, cudaStream_t st) {
-    LeafFusedArgs a{};
-    a.z = z; a.c2 = c2; a.BUpar = BUpar; a.U = U; a.mean = mean;
-    return launch_leaf_fused(m, B, LF_DOWN, a, st);
+    FusedArgs a{};
+    a.level = m->d.L; a.z = z; a.c2 = c2; a.BUpar = BUpar; a.U = U; a.mean = mean;
+    return launch_fused(m, B, LF_DOWN, m->d.n_leaves, a, st);
+}
+
+int ghm_wide_down_fused(const ghm_model* m, int64_t B, int level, const float* BUpar, const float* U, const float* H, float* BU,
+                        cudaStream_t st) {
+    FusedArgs a{};
+    a.level = level; a.BUpar = BUpar; a.U = U; a.H = H; a.out = BU;
+    return launch_fused(m, B, LF_DOWN_INT, m->d.spow[level], a, st);
 }
