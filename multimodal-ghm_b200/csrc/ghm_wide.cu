@@ -377,11 +377,16 @@ int ghm_wide_bp_cls(const ghm_model* m, int64_t B, const void* leaves, int leaf_
     float* U = H + n1 * B * d.QW;
     return dispatch_nv(d.QW, [&](auto nvc) -> int {
         constexpr int NV = decltype(nvc)::value;
-        k_wide_leaf_cls<NV><<<row_grid(n1 * B), WR_NT, 0, st>>>(d, B, leaves, leaf_dtype, H, post, root_hd);
-        GHM_CHECK_LAUNCH();
+        // TF32: the depth-(L-1) messages are formed inside the first GEMM (ghm_wide_tc.cu, LF_CLS)
+        int fused = d.L >= 2 ? ghm_wide_cls_leaf_fused(m, B, leaves, leaf_dtype, U, st) : GHM_EUNSUP;
+        if (fused != GHM_OK && fused != GHM_EUNSUP) return fused;
+        if (fused == GHM_EUNSUP) {
+            k_wide_leaf_cls<NV><<<row_grid(n1 * B), WR_NT, 0, st>>>(d, B, leaves, leaf_dtype, H, post, root_hd);
+            GHM_CHECK_LAUNCH();
+        }
         for (int l = d.L - 1; l >= 1; --l) {                   // H holds the depth-l messages
             const int n = d.spow[l];
-            int rc = ghm_wide_gemm(m, B, l, n, 0, H, U, st);
+            int rc = (fused == GHM_OK && l == d.L - 1) ? GHM_OK : ghm_wide_gemm(m, B, l, n, 0, H, U, st);
             if (rc) return rc;
             const int np = d.spow[l - 1];
             k_wide_combine<NV><<<row_grid((int64_t)np * B), WR_NT, 0, st>>>(d, B, np, U, l == 1 ? nullptr : H, nullptr,

@@ -23,3 +23,5 @@ int ghm_wide_leaf_down_fused(const ghm_model* m, int64_t B, const float* z, floa
 // internal level l of the downward pass: beliefs BU[l] = hd * (T^T (BU[l-1] / u)) / max in one kernel
 int ghm_wide_down_fused(const ghm_model* m, int64_t B, int level, const float* BUpar, const float* U, const float* H, float* BU,
                         cudaStream_t st);
+// BP_CLS, depth L-1 (s <= 3): the leaf-row products are formed inside the GEMM, U[j] = T_j h_j comes out directly
+int ghm_wide_cls_leaf_fused(const ghm_model* m, int64_t B, const void* leaves, int leaf_dtype, float* U, cudaStream_t st);

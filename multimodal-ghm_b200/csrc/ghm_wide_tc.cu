@@ -505,6 +505,8 @@ __global__ void __launch_bounds__(TMA_THREADS) k_wide_gemm_tma_mc(const __grid_c
 // a warp covers 4 tile rows x 128 bytes and writes each 16-byte piece to its SWIZZLE_128B slot):
 //   LF_UP       : A[r][k] = exp2(c2 ((z_r - k)^2 - d0_r))  from one float per row   (reference :485)
 //   LF_DOWN(_INT): A[r][k] = b_parent[r][k] / u_v[r][k]                              (reference :513)
+//   LF_CLS      : A[r][k] = prod_c T_c[k][x_c(r)]  (BP_CLS, depth L-1: the leaf rows gathered from the L2-resident table,
+//                 :191-196; left unnormalised -- the scale is removed by the combine that follows the GEMM)
 // the weight still arrives by TMA, and the same eight warps run the epilogue on the TMEM accumulator:
 //   LF_UP       : store u = T e (transposed to coalesced rows);
 //   LF_DOWN     : posterior mean sum_k k e_k tt_k / sum_k e_k tt_k reduced in registers (:516-519);
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(TMA_THREADS) k_wide_gemm_tma_mc(const __grid_c
 //                 two warps of a lane quarter, second pass rescales and stores.
 // Nothing but the inputs and the outputs of a level crosses HBM.
 // ------------------------------------------------------------------------------------------------
-enum { LF_UP = 0, LF_DOWN = 1, LF_DOWN_INT = 2 };
+enum { LF_UP = 0, LF_DOWN = 1, LF_DOWN_INT = 2, LF_CLS = 3 };
 #define FUSED_PROD_WARPS 8
 #define FUSED_THREADS (64 + 32 * FUSED_PROD_WARPS)
 struct FusedArgs {
@@ -524,6 +526,8 @@ struct FusedArgs {
     const float* H;          // [n][B][N]     hd of the nodes                 (LF_DOWN_INT)
     float* out;              // [n][B][N]     LF_UP: u;  LF_DOWN_INT: beliefs
     float* mean;             // [B][nL]       (LF_DOWN)
+    const void* leaves;      // [B][nL] int64 / uint8          (LF_CLS)
+    int leaf_dtype;
 };
 
 __device__ __forceinline__ float ex2_fast(float x) {          // arguments <= 0: MUFU.EX2, flushes to 0 far below 2^-126
@@ -605,19 +609,51 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_wide_fused(const __grid_const
         const int64_t b = m0 + r;
         const bool ok = b < B;
         float zi = 0.f, d0 = 0.f;
-        if (MODE != LF_DOWN_INT) {
+        if (MODE == LF_UP || MODE == LF_DOWN) {
             zi = ok ? a.z[b * nL + node] : 0.f;
             const float kstar = fminf(fmaxf(rintf(zi), 0.f), (float)(q - 1));
             d0 = (zi - kstar) * (zi - kstar);
         }
         const int pc = lane & 7;
         const int par = ghm_div_s(node, d);
+        // LF_CLS: table row (matrix of leaf edge c, leaf state x_c) of each of the 4 tile rows this lane produces, c < s
+        const float* crow[4][3];
+        int s_cls = 0;
+        if (MODE == LF_CLS) {
+            s_cls = d.s;                                      // host: s <= 3 for this mode
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rr = quarter * 32 + 16 * half + 4 * i + (lane >> 3);
+                const int64_t bc = min(m0 + rr, B - 1);
+                for (int c = 0; c < 3; ++c) {
+                    crow[i][c] = nullptr;
+                    if (c < s_cls) {
+                        const int leaf = node * s_cls + c;
+                        int64_t x = a.leaf_dtype == GHM_LEAF_I64 ? reinterpret_cast<const int64_t*>(a.leaves)[bc * nL + leaf]
+                                                                 : (int64_t) reinterpret_cast<const uint8_t*>(a.leaves)[bc * nL + leaf];
+                        if (x < 0 || x >= q) { atomicOr(d.status, 1); x = x < 0 ? 0 : q - 1; }
+                        const int ml = d.mat_off[d.L] + (d.ti ? c : leaf);
+                        crow[i][c] = d.Wdn + ((size_t)ml * N + (int)x) * N;          // T[:, x] of that edge
+                    }
+                }
+            }
+        }
         for (int kc = 0; kc < nchunks; ++kc) {
             const int st = kc % stages;
             if (kc >= stages) mbar_wait(&empty_bar[st], ((kc / stages) - 1) & 1);
             unsigned char* At = tiles + (size_t)st * stage_bytes;
             float4 pbv[4], puv[4];
-            if (MODE != LF_UP) {                                         // all 8 loads of the chunk in flight before any use
+            if (MODE == LF_CLS) {                                        // gathered rows: pbv = row of child 0 (x child 1), puv = child 2
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    pbv[i] = __ldg(reinterpret_cast<const float4*>(crow[i][0] + kc * 32) + pc);
+                    if (s_cls > 1) {
+                        const float4 t1 = __ldg(reinterpret_cast<const float4*>(crow[i][1] + kc * 32) + pc);
+                        pbv[i].x *= t1.x; pbv[i].y *= t1.y; pbv[i].z *= t1.z; pbv[i].w *= t1.w;
+                    }
+                    puv[i] = s_cls > 2 ? __ldg(reinterpret_cast<const float4*>(crow[i][2] + kc * 32) + pc) : make_float4(1.f, 1.f, 1.f, 1.f);
+                }
+            } else if (MODE != LF_UP) {                                  // all 8 loads of the chunk in flight before any use
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int rr = quarter * 32 + 16 * half + 4 * i + (lane >> 3);
@@ -642,6 +678,10 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_wide_fused(const __grid_const
                         e[x] = (in && k < q) ? ex2_fast(a.c2 * (dk * dk - dr)) : 0.f;
                     }
                     v = make_uint4(__float_as_uint(e[0]), __float_as_uint(e[1]), __float_as_uint(e[2]), __float_as_uint(e[3]));
+                } else if (MODE == LF_CLS) {
+                    const float4 pb = pbv[i], pu = puv[i];
+                    v = make_uint4(__float_as_uint(in ? pb.x * pu.x : 0.f), __float_as_uint(in ? pb.y * pu.y : 0.f),
+                                   __float_as_uint(in ? pb.z * pu.z : 0.f), __float_as_uint(in ? pb.w * pu.w : 0.f));
                 } else {
                     const float4 pb = pbv[i], pu = puv[i];
                     v = make_uint4(__float_as_uint(in && pu.x > 0.f ? __fdividef(pb.x, pu.x) : 0.f),
@@ -659,7 +699,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_wide_fused(const __grid_const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* stage_f = reinterpret_cast<float*>(tiles);
         const uint32_t tlane = tmem_d + ((uint32_t)(quarter * 32) << 16);
-        if (MODE == LF_UP) {
+        if (MODE == LF_UP || MODE == LF_CLS) {
             epilogue_store_rows(tmem_d, quarter, lane, N, m0, B, a.out + (int64_t)node * B * N, stage_f, pid, 32 * half, 64);
         } else if (MODE == LF_DOWN) {
             float num = 0.f, den = 0.f;
@@ -836,13 +876,14 @@ static int launch_fused(const ghm_model* m, int64_t B, int mode, int n_nodes, co
     const int N = d.QW;
     if (m->gemm_mode != GHM_GEMM_TF32) return GHM_EUNSUP;
     if (const char* e = getenv("GHM_WIDE_UNFUSED")) {          // development switch: "1" = all, "up" / "down" / "int" = one mode
-        if (e[0] == '1' || (e[0] == 'u' && mode == LF_UP) || (e[0] == 'd' && mode == LF_DOWN) || (e[0] == 'i' && mode == LF_DOWN_INT))
+        if (e[0] == '1' || (e[0] == 'u' && mode == LF_UP) || (e[0] == 'd' && mode == LF_DOWN) || (e[0] == 'i' && mode == LF_DOWN_INT) ||
+            (e[0] == 'c' && mode == LF_CLS))
             return GHM_EUNSUP;
     }
     if (N != 64 && N != 128 && N != 192 && N != 256) return GHM_EUNSUP;
     if (n_nodes > 65535) return GHM_EUNSUP;
     CUtensorMap mapW;
-    if (!make_map(&mapW, mode == LF_UP ? d.Wup : d.Wdn, (uint64_t)d.n_mat * (uint64_t)N, N, N)) return GHM_EUNSUP;
+    if (!make_map(&mapW, (mode == LF_UP || mode == LF_CLS) ? d.Wup : d.Wdn, (uint64_t)d.n_mat * (uint64_t)N, N, N)) return GHM_EUNSUP;
     const int stage_bytes = TC_M * 128 + N * 128;
     int stages = std::min(4, N / 32);
     while (stages > 2 && (size_t)stages * stage_bytes + 1024 > 110 * 1024) --stages;     // two CTAs per SM
@@ -856,6 +897,7 @@ static int launch_fused(const ghm_model* m, int64_t B, int mode, int n_nodes, co
     };
     if (mode == LF_UP) return go(k_wide_fused<LF_UP>);
     if (mode == LF_DOWN) return go(k_wide_fused<LF_DOWN>);
+    if (mode == LF_CLS) return go(k_wide_fused<LF_CLS>);
     return go(k_wide_fused<LF_DOWN_INT>);
 }
 
@@ -877,4 +919,12 @@ int ghm_wide_down_fused(const ghm_model* m, int64_t B, int level, const float* B
     FusedArgs a{};
     a.level = level; a.BUpar = BUpar; a.U = U; a.H = H; a.out = BU;
     return launch_fused(m, B, LF_DOWN_INT, m->d.spow[level], a, st);
+}
+
+// BP_CLS, depth L-1: U[j] = T_j (prod_c T_c[:, x_c]) with the leaf-row product formed inside the GEMM's A producer
+int ghm_wide_cls_leaf_fused(const ghm_model* m, int64_t B, const void* leaves, int leaf_dtype, float* U, cudaStream_t st) {
+    if (m->d.s > 3 || m->d.L < 2) return GHM_EUNSUP;
+    FusedArgs a{};
+    a.level = m->d.L - 1; a.leaves = leaves; a.leaf_dtype = leaf_dtype; a.out = U;
+    return launch_fused(m, B, LF_CLS, m->d.spow[m->d.L - 1], a, st);
 }
