@@ -56,14 +56,15 @@ METRIC = "JGHM trees/sec (sample + full BP posterior)"
 N_SM = 148
 # Figures of the dominant kernel taken from its committed `ncu --set full` capture (per launch of 327 680 trees)
 KTREE = {
-    "kernel": "k_tree2<Q=10,S=3,TPT=2,PHILOX,BP> (fused sampler + root-posterior BP, int64 leaves out)",
-    "source": "profiles/r01f_ncu_full_k_tree2.csv",
-    "dram_bytes_per_tree": 523.2,          # 171.37 MB written + 0.08 MB read per launch (below the 696 B/tree algorithmic
+    "kernel": "k_tree_fast<Q=10,S=3,PHILOX,BP> (fused sampler + root-posterior BP, two trees per thread, int64 leaves out)",
+    "source": "profiles/r02_ncu_full_k_tree_fast.csv",
+    "dram_bytes_per_tree": 518.8,          # 169.92 MB written + 0.09 MB read per launch (below the 696 B/tree algorithmic
                                            # figure: the tail of the leaves is still in the 126 MB L2 when the kernel ends)
-    "warp_inst_per_tree": 112995840 / 327680,
+    "warp_inst_per_tree": 106626560 / 327680,
     "share": 0.955,
-    "note": "issue-slot / FP32-pipe bound by design (Philox IMAD.WIDE chains, alias draws, packed FFMA2 BP); the HBM "
-            "fraction is reported, not padded; see roofline.secondary",
+    "note": "no single unit is the wall: issue slots 0.60, FMA-heavy pipe 0.54 (FFMA2 2.1 clk, Philox IMAD.WIDE 4.3 clk per warp "
+            "instruction), ALU pipe 0.35, shared-memory pipe 0.52 at 4 warps per scheduler (123 registers, 54 KB); a fifth CTA "
+            "per SM measured 7 % SLOWER; the HBM fraction is reported, not padded; see roofline.secondary and DESIGN.md 3.1",
 }
 
 

@@ -23,6 +23,13 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
     constexpr int TPT = 2, NT = T2_NT, H = Q / 2, QS = (Q + 3) / 4 * 4, WTREES = 32 * TPT;
     constexpr bool SPARE = (S & 3) != 0;                         // node j is drawn from the spare word of its leaf block
     constexpr bool PHILOX = MODE == MODE_PHILOX;
+    // Shared-memory stride of the gathered leaf rows T_c^T[x, :].  Each lane reads the row of ITS leaf state, so the
+    // loads are true gathers: with 48-byte rows read as LDS.128 + LDS.128 + LDS.64 the ten rows of q = 10 fall on eight
+    // 16-byte bank groups (rows 0/8 and 1/9 collide: 0.5 extra wavefronts per load, ncu r02k); with 40-byte rows read
+    // as five LDS.64 the ten rows start on ten different 8-byte bank groups (10 x mod 32 = 0,10,20,30,8,18,28,6,16,26).
+    // Measured (B = 327 680, L4 s3 q10): BP on given leaves 0.122 -> 0.117 ms, but the fused Philox variant 0.166 -> 0.175 ms
+    // (the extra LDS.64 issue slots and 3 more registers cost more there than the conflicts), so only MODE_GIVEN uses it.
+    constexpr int LS = (Q % 4 == 2 && MODE == MODE_GIVEN) ? Q : QS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = d.L, q = d.q, nL = d.n_leaves;                 // L >= 3 (host)
     const int64_t warp_tree0 = ((int64_t)blockIdx.x * T2_WARPS + warp) * WTREES;
@@ -34,10 +41,10 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
     const uint32_t* AL = d.alias;
     if (BP) {                                                    // leaf-level T^T rows are gathered per lane by leaf state
         const int first = d.mat_off[L];
-        const int words = S * Q * QS;
-        float* s1 = reinterpret_cast<float*>(smem + off); off += (size_t)words * 4;
+        const int words = S * Q * LS;
+        float* s1 = reinterpret_cast<float*>(smem + off); off += ((size_t)words * 4 + 15) / 16 * 16;
         const float* src = d.TTp + (size_t)first * Q * QS;
-        for (int i = tid; i < words; i += NT) s1[i] = src[i];
+        for (int i = tid; i < words; i += NT) s1[i] = src[(i / LS) * QS + (i % LS)];
         tt_leaf0 = s1;
     }
     if (PHILOX) {
@@ -165,7 +172,13 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
                 }
                 if (BP) {
                     f2 row[H];
-                    f2_load_row<Q>(tt_leaf0 + (c * Q + x) * QS, row);
+                    if constexpr (LS == Q) {
+                        const f2* rp = reinterpret_cast<const f2*>(tt_leaf0 + (c * Q + x) * LS);
+#pragma unroll
+                        for (int i = 0; i < H; ++i) row[i] = rp[i];
+                    } else {
+                        f2_load_row<Q>(tt_leaf0 + (c * Q + x) * QS, row);
+                    }
 #pragma unroll
                     for (int i = 0; i < H; ++i) hout[t][i] = c == 0 ? row[i] : f2_mul(hout[t][i], row[i]);
                 }
@@ -305,7 +318,7 @@ static int launch_tree_fast(const ghm_model* m, const TreeArgs& a0, cudaStream_t
     constexpr int QS = (Q + 3) / 4 * 4, WTREES = 64;
     const int n_deep = d.L - 2;
     size_t dyn = 0;
-    if (BP) dyn += (size_t)S * Q * QS * 4;
+    if (BP) dyn += ((size_t)S * Q * ((Q % 4 == 2 && MODE == MODE_GIVEN) ? Q : QS) * 4 + 15) / 16 * 16;
     if (MODE == MODE_PHILOX) dyn += ((size_t)d.n_mat * d.q * d.q * 4 + 15) / 16 * 16;
     if (BP) dyn += (size_t)n_deep * (Q / 2) * 2 * T2_NT * sizeof(float2);
     if (MODE == MODE_PHILOX) {
