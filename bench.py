@@ -524,7 +524,14 @@ def strong_scaling(args, rank, world, dev, barrier):
             return e0.elapsed_time(e1) / reps, h
 
         reps = 3 if q <= 16 else 1
+        if os.environ.get("GHM_BENCH_DEBUG"):
+            st0 = torch.cuda.memory_stats(dev)
         ms, h = timed(world > 1, reps)
+        if os.environ.get("GHM_BENCH_DEBUG"):
+            st1 = torch.cuda.memory_stats(dev)
+            sys.stderr.write("strong %s: %.3f ms; device allocs %d -> %d, frees %d -> %d, retries %d, reserved %.1f GB\n" % (
+                tag, ms, st0["num_device_alloc"], st1["num_device_alloc"], st0["num_device_free"], st1["num_device_free"],
+                st1["num_alloc_retries"], st1["reserved_bytes.all.current"] / 1e9))
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -114,6 +114,17 @@ GHM_API int ghm_sample_mixed(const ghm_model_t* m, int64_t B, int64_t n_given, c
  * [0, n_shared) re-draw the uniform root the partner modality drew (Philox key `root_seed` = the partner's seed,
  * same global tree index), trees [n_shared, B) draw their own uniform roots.  The two modalities can then be
  * launched on different streams and their CTAs fill each other's tail waves.  Philox mode only. */
+/* A SHARD of a block-structured batch in one launch: local tree b has the global Philox index
+ * tree_offset + (b / blk_len) * blk_stride + b % blk_len.  ClipSampler's layout [match1 | match2 | K-1 negatives] (:758-764)
+ * sharded on the pair index (pairs [lo, hi) of n on this rank) is blk_len = hi - lo, blk_stride = n, tree_offset = base + lo:
+ * the rank draws exactly the trees the unsharded launch would have drawn for those pairs.  root_mode as ghm_sample
+ * (GHM_ROOT_GIVEN: every root from root_in) or GHM_ROOT_SHARED with n_given local trees re-drawing the partner's roots
+ * (ghm_sample_paired).  Philox mode only. */
+GHM_API int ghm_sample_blocked(const ghm_model_t* m, int64_t B, int64_t blk_len, int64_t blk_stride, int root_mode,
+                       int64_t n_given, const int64_t* root_in, uint64_t root_seed, uint64_t seed, uint64_t tree_offset,
+                       int64_t* root_out, void* leaves_out, int leaf_dtype, float* post_out, float* root_hd_out,
+                       void* stream);
+
 GHM_API int ghm_sample_paired(const ghm_model_t* m, int64_t B, int64_t n_shared, uint64_t root_seed, uint64_t seed,
                       uint64_t tree_offset, int64_t* root_out, void* leaves_out, int leaf_dtype,
                       float* post_out, float* root_hd_out, void* stream);

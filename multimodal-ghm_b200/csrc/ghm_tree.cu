@@ -90,7 +90,8 @@ struct DeviceGuard {
 
 static int sample_common(const ghm_model_t* m, int64_t B, int root_mode, int64_t n_given, const int64_t* root_in,
                          uint64_t root_seed, const double* U, uint64_t seed, uint64_t tree_offset, int64_t* root_out, void* leaves_out,
-                         int leaf_dtype, float* post_out, float* root_hd_out, void* stream) {
+                         int leaf_dtype, float* post_out, float* root_hd_out, void* stream, int64_t blk_len = 0,
+                         int64_t blk_stride = 0) {
     if (!m) return ghm_fail(GHM_EINVAL, "ghm_sample: null model");
     if (B <= 0) return B == 0 ? GHM_OK : ghm_fail(GHM_EINVAL, "ghm_sample: negative batch");
     if (root_mode < 0 || root_mode > 3) return ghm_fail(GHM_EINVAL, "ghm_sample: bad root_mode %d", root_mode);
@@ -104,6 +105,7 @@ static int sample_common(const ghm_model_t* m, int64_t B, int root_mode, int64_t
     a.B = B; a.root_mode = root_mode; a.n_given = n_given; a.root_in = root_in; a.root_seed = root_seed; a.U = U;
     a.seed = seed;
     a.tree_offset = tree_offset;
+    a.blk_len = blk_len; a.blk_stride = blk_stride;
     a.root_out = root_out; a.leaves = leaves_out; a.leaf_dtype = leaf_dtype; a.post = post_out; a.root_hd = root_hd_out;
     const bool bp = post_out || root_hd_out;
     if (bp && m->d.QW)
@@ -140,6 +142,17 @@ extern "C" int ghm_sample_paired(const ghm_model_t* m, int64_t B, int64_t n_shar
                                  float* post_out, float* root_hd_out, void* stream) {
     return sample_common(m, B, GHM_ROOT_SHARED, n_shared, nullptr, root_seed, nullptr, seed, tree_offset, root_out,
                          leaves_out, leaf_dtype, post_out, root_hd_out, stream);
+}
+
+extern "C" int ghm_sample_blocked(const ghm_model_t* m, int64_t B, int64_t blk_len, int64_t blk_stride, int root_mode,
+                                  int64_t n_given, const int64_t* root_in, uint64_t root_seed, uint64_t seed, uint64_t tree_offset,
+                                  int64_t* root_out, void* leaves_out, int leaf_dtype, float* post_out, float* root_hd_out,
+                                  void* stream) {
+    if (blk_len <= 0 || blk_stride < blk_len) return ghm_fail(GHM_EINVAL, "ghm_sample_blocked: need 0 < blk_len <= blk_stride");
+    if (root_mode == GHM_ROOT_GIVEN && n_given != B && n_given != 0)
+        return ghm_fail(GHM_EINVAL, "ghm_sample_blocked: GHM_ROOT_GIVEN takes all roots (n_given = B) or none");
+    return sample_common(m, B, root_mode, root_mode == GHM_ROOT_GIVEN ? B : n_given, root_in, root_seed, nullptr, seed, tree_offset,
+                         root_out, leaves_out, leaf_dtype, post_out, root_hd_out, stream, blk_len, blk_stride);
 }
 
 extern "C" int64_t ghm_bp_cls_workspace_bytes(const ghm_model_t* m, int64_t B) {

@@ -76,7 +76,7 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
         bt[t] = warp_tree0 + 32 * t + lane;
         active[t] = bt[t] < a.B;
         const int64_t bc = active[t] ? bt[t] : a.B - 1;          // tail threads shadow the last tree and never write
-        tree[t] = a.tree_offset + (uint64_t)bc;
+        tree[t] = a.tree_offset + (uint64_t)(a.blk_len > 0 ? (bc / a.blk_len) * a.blk_stride + bc % a.blk_len : bc);
         srow[t] = (32 * t + lane) * nL;
     }
     if (!PHILOX) stage_load_flat(stage, WTREES, a.leaves, a.leaf_dtype, warp_tree0, a.B, nL, lane, q, d.status);

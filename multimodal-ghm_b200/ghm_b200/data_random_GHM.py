@@ -22,6 +22,8 @@ Deliberate deviations, each mirrored from SURVEY.md section 8 / Appendix A:
   * ``Node`` objects exist for ``root_node`` / ``leaves_nodes`` only (no per-node message graph).
   * ``BP_dummy_NWP`` / ``BP_NWP`` (dead code upstream, :223-334) raise NotImplementedError.
 """
+import weakref
+
 import numpy as np
 import torch
 import torch.nn as nn  # noqa: F401  (the reference re-exports these through `import *`)
@@ -183,7 +185,17 @@ class _RootLevel:
     that sampling a tree never synchronises the host (the training feed)."""
 
     def __init__(self, tree):
-        self._tree = tree
+        # weak: the tree owns this object (tree.T_value[0]); a strong back-reference would make every GHMTree a
+        # reference cycle, and its device tensors (170 MB of leaves per 262 144 trees) would then wait for the cyclic
+        # garbage collector instead of being recycled by the caching allocator as soon as the tree is dropped
+        self._tree_ref = weakref.ref(tree)
+
+    @property
+    def _tree(self):
+        t = self._tree_ref()
+        if t is None:
+            raise ReferenceError("the GHMTree this root level belongs to has been released")
+        return t
 
     def __len__(self):
         return 1
@@ -747,19 +759,21 @@ class ClipSampler(DoubleSampler):
              "root": torch.empty(Bl, dtype=torch.int64, device=dev),
              "post": torch.empty((Bl, q), dtype=torch.float32, device=dev) if want_post else None}
         iseed = self.seed ^ ops.IMAGE_SEED_XOR
-
-        def sl(x, j):
-            return None if x is None else x[j * nl:(j + 1) * nl]
-        for j in range(K + 1):
-            goff = off + j * n + pair_lo
-            ops.sample_into(self.t_model, nl, ops.ROOT_UNIFORM, None, self.seed, goff, sl(t["root"], j),
-                            sl(t["leaves"], j), sl(t["post"], j), None)
-            if j < 2:
-                ops.sample_into(self.i_model, nl, ops.ROOT_GIVEN, sl(t["root"], j), iseed, goff, sl(i["root"], j),
-                                sl(i["leaves"], j), sl(i["post"], j), None)
-            else:
-                ops.sample_into(self.i_model, nl, ops.ROOT_UNIFORM, None, iseed, goff, sl(i["root"], j),
-                                sl(i["leaves"], j), sl(i["post"], j), None)
+        # One launch per modality for the whole shard (ghm_sample_blocked: block j of the local batch is pairs [lo, hi) of
+        # block j of the global layout), image roots of the two matched blocks re-drawn from the text key: the two launches
+        # are independent and overlap on two streams exactly like the unsharded path.
+        cur = torch.cuda.current_stream(dev)
+        side = self._side_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            ops.sample_blocked_into(self.i_model, Bl, nl, n, ops.ROOT_SHARED, 2 * nl, None, self.seed, iseed, off + pair_lo,
+                                    i["root"], i["leaves"], i["post"], None)
+        ops.sample_blocked_into(self.t_model, Bl, nl, n, ops.ROOT_UNIFORM, 0, None, 0, self.seed, off + pair_lo,
+                                t["root"], t["leaves"], t["post"], None)
+        cur.wait_stream(side)
+        for x in (i["root"], i["leaves"], i["post"]):
+            if x is not None:
+                x.record_stream(side)
         return {"t": t, "i": i, "n_local": nl}
 
     def get_batch(self, device="cpu", batch_size=128, guide=False, async_=False):

@@ -13,7 +13,7 @@ import torch
 from ._lib import check, get_lib
 
 LEAF_I64, LEAF_U8 = 0, 1
-ROOT_GIVEN, ROOT_PRIOR, ROOT_UNIFORM = 0, 1, 2
+ROOT_GIVEN, ROOT_PRIOR, ROOT_UNIFORM, ROOT_SHARED = 0, 1, 2, 3
 
 
 def _ptr(t):
@@ -316,6 +316,19 @@ def sample_paired_into(model, batch, n_shared, root_seed, seed, tree_offset, roo
                                            _ptr(root_out), _ptr(leaves_out),
                                            _leaf_code(leaves_out) if leaves_out is not None else LEAF_I64,
                                            _ptr(post_out), _ptr(root_hd_out), _stream()))
+
+
+def sample_blocked_into(model, batch, blk_len, blk_stride, root_mode, n_given, root_in, root_seed, seed, tree_offset, root_out,
+                        leaves_out, post_out, root_hd_out):
+    """ghm_sample_blocked: one launch for a shard of a block-structured batch (local tree b -> global Philox index
+    tree_offset + (b // blk_len) * blk_stride + b % blk_len)."""
+    for t in (root_in, root_out, leaves_out, post_out, root_hd_out):
+        assert t is None or t.is_contiguous()
+    with _on(model.device):
+        check(model._lib.ghm_sample_blocked(model._h, int(batch), int(blk_len), int(blk_stride), int(root_mode), int(n_given),
+                                            _ptr(root_in), root_seed, seed, tree_offset, _ptr(root_out), _ptr(leaves_out),
+                                            _leaf_code(leaves_out) if leaves_out is not None else LEAF_I64,
+                                            _ptr(post_out), _ptr(root_hd_out), _stream()))
 
 
 def new_sums(device):

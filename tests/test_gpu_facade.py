@@ -117,6 +117,19 @@ def test_philox_clip_bayes_statistical_and_sharded(G, kat):
         rr = s2._sample_layout(n, want_leaves=False, want_post=True, pair_lo=lo, pair_hi=hi)
         ops.risk_clip(rr["t"]["post"], rr["i"]["post"], hi - lo, 4, 10, sums=tot)
     assert mean_se_from_sums(tot)[0] == pytest.approx(float(whole), rel=1e-12)
+    # the shard is ONE launch per modality (ghm_sample_blocked): its rows are bit-identical to the rows of the whole layout
+    import torch
+    K = 4
+    s3 = G.ClipSampler([4, 4], [3, 3], [u10, u10], [.2, .2], rng="philox", seed=9)
+    full = s3._sample_layout(n, want_leaves=True, want_post=True)
+    lo, hi = shard_range(n, 1, 3)
+    s4 = G.ClipSampler([4, 4], [3, 3], [u10, u10], [.2, .2], rng="philox", seed=9)
+    part = s4._sample_layout(n, want_leaves=True, want_post=True, pair_lo=lo, pair_hi=hi)
+    torch.cuda.synchronize()
+    rows = torch.cat([torch.arange(j * n + lo, j * n + hi) for j in range(K + 1)]).cuda()
+    for side in ("t", "i"):
+        for key in ("root", "leaves", "post"):
+            assert torch.equal(part[side][key], full[side][key][rows]), (side, key)
 
 
 def test_kat_cdm_bayes(G, kat):
