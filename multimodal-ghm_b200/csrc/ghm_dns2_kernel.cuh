@@ -27,16 +27,27 @@ struct Dns2Args {
     int dn_off;                                        // float offset of the Tlin block inside the table parameter
 };
 
-template <int Q>
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(d);
+}
+
+// Gaussian leaf likelihoods e[k] = exp2(c2 ((z - k)^2 - d0)), shifted so that the nearest state has e = 1 (:485).
+// Packed f32x2 arithmetic: three packed instructions + two MUFU.EX2 per state pair (the scalar form was 14 and, with
+// 162 calls per tree, 14 % of k_dns2's instructions).  EX: q == Q, no padding states to mask.
+template <int Q, bool EX>
 __device__ __forceinline__ void f2_leaf_like(float z, float c2, int q, f2 (&e)[Q / 2]) {
     float kstar = rintf(z);
     kstar = fminf(fmaxf(kstar, 0.f), (float)(q - 1));
     const float d0 = (z - kstar) * (z - kstar);
+    const f2 zz = make_float2(z, z), cc = make_float2(c2, c2), dd = make_float2(-d0, -d0);
 #pragma unroll
     for (int i = 0; i < Q / 2; ++i) {
-        const float da = z - (float)(2 * i), db = z - (float)(2 * i + 1);
-        e[i].x = (2 * i < q) ? ex2_approx(c2 * (da * da - d0)) : 0.f;
-        e[i].y = (2 * i + 1 < q) ? ex2_approx(c2 * (db * db - d0)) : 0.f;
+        const f2 da = f2_add(zz, make_float2(-(float)(2 * i), -(float)(2 * i + 1)));
+        const f2 arg = f2_mul(f2_fma(da, da, dd), cc);
+        e[i].x = (EX || 2 * i < q) ? ex2_approx(arg.x) : 0.f;
+        e[i].y = (EX || 2 * i + 1 < q) ? ex2_approx(arg.y) : 0.f;
     }
 }
 
@@ -91,7 +102,6 @@ k_dns2(const __grid_constant__ GhmDev d, const __grid_constant__ Dns2Args aa, co
     f2 msg[H], accT[H];
 #pragma unroll
     for (int i = 0; i < H; ++i) { msg[i] = make_float2(0.f, 0.f); accT[i] = make_float2(0.f, 0.f); }
-    unsigned long long D = 0;                                      // base-s digits of j, 4 bits per depth (vector side)
     int cj = 0;
     const int base0 = aa.base0, base1 = aa.base1;
     int toff0 = base0, toff1 = base1;                              // uniform-side twins: matrix index of the two hottest steps
@@ -103,18 +113,13 @@ k_dns2(const __grid_constant__ GhmDev d, const __grid_constant__ Dns2Args aa, co
             toff1 += 1;
             if (toff1 == base1 + s) toff1 = base1;
         }
-        for (int l = L - 1; l >= 1; --l) {
-            const int c = (int)((D >> (4 * l)) & 15ull) + 1;
-            if (c < s) { D += 1ull << (4 * l); break; }
-            D &= ~(15ull << (4 * l));
-        }
     };
     for (int j = 0; j < n1; ++j) {
         f2 h[H];
 #pragma unroll
         for (int c = 0; c < S; ++c) {
             f2 e[H], u[H];
-            f2_leaf_like<Q>(zrow[j * S + c], a.c2, q, e);
+            f2_leaf_like<Q, false>(zrow[j * S + c], a.c2, q, e);
             f2_matvec_c<Q>(Tup + (aa.base_leaf + c) * QQ, e, u);
 #pragma unroll
             for (int i = 0; i < H; ++i) h[i] = c == 0 ? u[i] : f2_mul(h[i], u[i]);
@@ -152,7 +157,8 @@ k_dns2(const __grid_constant__ GhmDev d, const __grid_constant__ Dns2Args aa, co
         }
         if (up && L >= 4) {
             for (int l = L - 3; l > 0; --l) {
-                const int c = (int)((D >> (4 * l)) & 15ull);
+                const int pl = ghm_div_pow(j, L - 1 - l, d);               // path node at depth l (uniform datapath)
+                const int c = pl - (pl / S) * S;
                 if (!climb(Tup + ((l - 1) * s + c) * QQ, d.edge_off[l] + idx, c != 0, c == s - 1, stack + (size_t)(l - 1) * H * NT + tid))
                     break;
                 idx = idx / S;
@@ -182,7 +188,7 @@ k_dns2(const __grid_constant__ GhmDev d, const __grid_constant__ Dns2Args aa, co
     sstore(0, msg);                                                // beliefs per depth on the current path: stack[depth]
 
     // =============================== downward pass =============================================
-    D = 0; cj = 0; toff0 = base0; toff1 = base1;
+    cj = 0; toff0 = base0; toff1 = base1;
     float* mrow = a.mean + bc * nL;
     int tz = L > 2 ? L - 2 : 0;                                    // ancestors (depth 1..L-2) to refresh before node j
     for (int j = 0; j < n1; ++j) {
@@ -190,7 +196,7 @@ k_dns2(const __grid_constant__ GhmDev d, const __grid_constant__ Dns2Args aa, co
             // beliefs of the internal nodes of the root path that changed: depths L-1-tz .. L-2 (every s-th node at most)
             for (int l = L - 1 - tz; l <= L - 2; ++l) {
                 const int idx = ghm_div_pow(j, L - 1 - l, d);
-                const int c = (int)((D >> (4 * l)) & 15ull);
+                const int c = idx - (idx / S) * S;                        // child digit from the uniform index, not the vector odometer
                 f2 uv[H], hv[H], bp[H], w[H], tt[H];
                 uload(d.edge_off[l] + idx, uv);
                 for (int cc = 0; cc < S; ++cc) {
@@ -212,7 +218,7 @@ k_dns2(const __grid_constant__ GhmDev d, const __grid_constant__ Dns2Args aa, co
         f2 e[S][H], u[S][H], h[H];
 #pragma unroll
         for (int c = 0; c < S; ++c) {
-            f2_leaf_like<Q>(zrow[j * S + c], a.c2, q, e[c]);
+            f2_leaf_like<Q, false>(zrow[j * S + c], a.c2, q, e[c]);
             f2_matvec_c<Q>(Tup + (aa.base_leaf + c) * QQ, e[c], u[c]);
 #pragma unroll
             for (int i = 0; i < H; ++i) h[i] = c == 0 ? u[c][i] : f2_mul(h[i], u[c][i]);
@@ -249,13 +255,12 @@ k_dns2(const __grid_constant__ GhmDev d, const __grid_constant__ Dns2Args aa, co
         // advance the odometer; tz = number of depths <= L-2 that change before the next node
         advance();
         tz = 0;
-        if (cj == 0) {
-            tz = 1;
-            for (int l = L - 2; l >= 2; --l) {                     // digit l wrapped to 0 -> depth l-1 changes too
-                if (((D >> (4 * l)) & 15ull) != 0) break;
+        if (cj == 0) {                                             // depth l changes before node j+1 iff s^(L-1-l) divides j+1
+            const int jn = j + 1;
+            for (int l = L - 2; l >= 1; --l) {
+                if (ghm_div_pow(jn, L - 1 - l, d) * d.spow[L - 1 - l] != jn) break;
                 ++tz;
             }
-            tz = min(tz, L > 2 ? L - 2 : 0);
         }
     }
 }

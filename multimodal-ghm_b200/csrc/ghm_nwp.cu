@@ -279,10 +279,36 @@ k_nwp_full_u(const __grid_constant__ GhmDev d, const __grid_constant__ NwpArgs a
         const float* src = d.TlinT + (size_t)d.mat_off[L] * QQ;
         for (int i = tid; i < s * QQ; i += NWP_NT) LT[i] = __ldg(src + i);
     }
+    // The CTA's leaves as bytes in shared memory, [tree][n_L], read from the global [B, n_L] tensor as ONE contiguous span
+    // with consecutive threads on consecutive elements.  Each thread reading its own row (n_L int64 at an 8 n_L-byte stride
+    // between lanes) left this kernel waiting on those loads for 69 % of its samples (profiles/r02_ncu_full_k_nwp_full_u.csv).
+    uint8_t* LV = reinterpret_cast<uint8_t*>(nsm) + (((size_t)s * QQ * sizeof(float) + 15) / 16 * 16);
+    {
+        const int64_t t0 = (int64_t)blockIdx.x * NWP_NT;
+        const int64_t cnt = min((int64_t)NWP_NT, a.B - t0) * nL;
+        bool bad = false;
+        if (a.leaf_dtype == GHM_LEAF_I64) {
+            const int64_t* src = reinterpret_cast<const int64_t*>(a.leaves) + t0 * nL;
+            for (int64_t i = tid; i < cnt; i += NWP_NT) {
+                int64_t v = src[i];
+                if (v < 0 || v >= d.q) { bad = true; v = v < 0 ? 0 : d.q - 1; }
+                LV[i] = (uint8_t)v;
+            }
+        } else {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(a.leaves) + t0 * nL;
+            for (int64_t i = tid; i < cnt; i += NWP_NT) {
+                int v = src[i];
+                if (v >= d.q) { bad = true; v = d.q - 1; }
+                LV[i] = (uint8_t)v;
+            }
+        }
+        if (bad) atomicOr(d.status, 1);
+    }
     __syncthreads();
     const int64_t b0 = (int64_t)blockIdx.x * NWP_NT + tid;
     const bool act = b0 < a.B;
     const int64_t b = act ? b0 : a.B - 1;
+    const uint8_t* lrow = LV + (size_t)(act ? tid : (int)(a.B - 1 - (int64_t)blockIdx.x * NWP_NT)) * nL;
     f2* FT = reinterpret_cast<f2*>(a.full);
     const int64_t B = a.B;
     int lbase = u.up0;                                        // matrices of the edges into depth l
@@ -296,7 +322,7 @@ k_nwp_full_u(const __grid_constant__ GhmDev d, const __grid_constant__ NwpArgs a
             for (int i = 0; i < H; ++i) h[i] = make_float2(1.f, 1.f);
             for (int cc = 0; cc < s; ++cc) {
                 f2 f[H];
-                if (l == L - 1) nwp_leaf_msg_s<Q>(LT, cc, nwp_leaf(a, d, b * nL + idx * s + cc), f);
+                if (l == L - 1) nwp_leaf_msg_s<Q>(LT, cc, (int)lrow[idx * s + cc], f);
                 else {
                     const f2* src = FT + (int64_t)(noff_c + idx * s + cc) * H * B + b;
 #pragma unroll
@@ -476,6 +502,8 @@ static int launch_nwp_u(const ghm_model* m, const NwpArgs& a, cudaStream_t st) {
     if (GUIDE) return GHM_EUNSUP;                             // guide rows of one position sit 4q(n_L-1) bytes apart between
                                                              // trees: the (tree, position)-per-thread kernel writes them better
     const size_t lt = ((size_t)d.s * Q * Q + 3) / 4 * 4 * sizeof(float);
+    const size_t lt_full = (lt + 15) / 16 * 16 + (size_t)NWP_NT * d.n_leaves;     // k_nwp_full_u: + the CTA's leaves as bytes
+    if (lt_full > 100 * 1024) return GHM_EUNSUP;
     const size_t dyn_pos = lt + ((size_t)2 * (d.L - 1) + NWP_PC) * (Q / 2) * NWP_NT * sizeof(float2) + (size_t)(NWP_PC + d.s) * NWP_NT;
     if (dyn_pos > 100 * 1024) return GHM_EUNSUP;
     const int npos = d.n_leaves - 1;
@@ -489,7 +517,8 @@ static int launch_nwp_u(const ghm_model* m, const NwpArgs& a, cudaStream_t st) {
     tab.v[0] = 0.f;
     memcpy(tab.v, m->h_TlinT, words * sizeof(float));
     memcpy(tab.v + words, m->h_Tlin, words * sizeof(float));
-    k_nwp_full_u<Q, NW><<<gx, NWP_NT, lt, st>>>(d, a, u, tab);
+    GHM_CUDA_TRY(cudaFuncSetAttribute(k_nwp_full_u<Q, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lt_full));
+    k_nwp_full_u<Q, NW><<<gx, NWP_NT, lt_full, st>>>(d, a, u, tab);
     GHM_CHECK_LAUNCH();
     GHM_CUDA_TRY(cudaFuncSetAttribute(k_nwp_pos_u<Q, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_pos));
     k_nwp_pos_u<Q, NW><<<dim3(gx, (unsigned)pg), NWP_NT, dyn_pos, st>>>(d, a, u, tab);
