@@ -254,3 +254,34 @@ def test_full_size_properties_c2(ops):
     acc = float((post.argmax(1) == a["root"]).float().mean())
     assert 0.5 < acc <= 1.0
     assert tm.status() == 0
+
+
+def test_sample_blocked_equals_block_wise_launches(ops):
+    """ghm_sample_blocked: local tree b of a shard has the global Philox index offset + (b // blk_len) * blk_stride + b % blk_len,
+    so one blocked launch equals one contiguous launch per block -- roots (uniform and given), leaves and fused posteriors."""
+    from oracle import ghm_oracle as O
+    L, s, q = 4, 3, 10
+    np.random.seed(42)
+    T = O.gen_transition(L, s, q, 0.2, 1.0, True)
+    m = ops.GhmModel(T, L, s, q, p_y=np.ones(q) / q, device="cuda:0")
+    n, nl, lo, nb = 1000, 137, 411, 5
+    B = nl * nb
+    dev = m.device
+    def bufs():
+        return (torch.empty(B, dtype=torch.int64, device=dev), torch.empty((B, m.n_leaves), dtype=torch.int64, device=dev),
+                torch.empty((B, q), dtype=torch.float32, device=dev))
+    r1, l1, p1 = bufs()
+    ops.sample_blocked_into(m, B, nl, n, ops.ROOT_UNIFORM, 0, None, 0, 77, 5000 + lo, r1, l1, p1, None)
+    r2, l2, p2 = bufs()
+    for j in range(nb):
+        sl = slice(j * nl, (j + 1) * nl)
+        ops.sample_into(m, nl, ops.ROOT_UNIFORM, None, 77, 5000 + lo + j * n, r2[sl], l2[sl], p2[sl], None)
+    assert torch.equal(r1, r2) and torch.equal(l1, l2) and torch.equal(p1, p2)
+    given = torch.randint(0, q, (B,), device=dev)
+    r3, l3, p3 = bufs()
+    ops.sample_blocked_into(m, B, nl, n, ops.ROOT_GIVEN, B, given, 0, 78, lo, r3, l3, p3, None)
+    r4, l4, p4 = bufs()
+    for j in range(nb):
+        sl = slice(j * nl, (j + 1) * nl)
+        ops.sample_into(m, nl, ops.ROOT_GIVEN, given[sl].contiguous(), 78, lo + j * n, r4[sl], l4[sl], p4[sl], None)
+    assert torch.equal(r3, given) and torch.equal(l3, l4) and torch.equal(p3, p4)

@@ -155,3 +155,25 @@ def test_wide_guides_cls_dns_vs_oracle(ops, L, s, q, ti, B, sigma):
         # leaf hd = -(z-k)^2 / 2 sigma^2 reaches -3e4 at q = 256: float32 resolution there is 2e-3, hence the relative bound
         _cmp_list(g, O.guides_dns(dhd, dqd, dbu, L, s), "dns", atol=1e-4)
     assert m.status() == 0
+
+
+def test_wide_tf32_fused_levels_per_edge_tables(ops):
+    """The fused TF32 kernels (likelihoods / cavities / beliefs / leaf-row products computed inside the GEMM) pick the weight
+    per NODE: a per-edge (non translation-invariant) model, ragged batch, s = 3, against the float64 oracle."""
+    from oracle import ghm_oracle as O
+    L, s, q, B = 3, 3, 64, 203
+    T, py, m = _model(ops, L, s, q, False, seed=21, p=0.3)
+    rng = np.random.RandomState(12)
+    vals = O.sample_tree(T, L, s, q, B, root=rng.randint(0, q, size=B), U=rng.rand(O.n_edges(L, s), B))
+    leaves = torch.from_numpy(vals[-1].T.copy()).cuda()
+    z = vals[-1] + 0.7 * rng.randn(s ** L, B)
+    zt = torch.from_numpy(z.T.astype(np.float32)).cuda().contiguous()
+    post, hd = O.bp_cls(T, vals[-1], L, s, q, py)
+    mean_ref = O.bp_dns(T, z, 0.7, L, s, q, ext=hd[0][0])[0]
+    m.set_gemm_mode(m.GEMM_TF32)
+    p, h = m.bp_cls(leaves)
+    np.testing.assert_allclose(p.cpu().numpy(), post.T, rtol=3e-3, atol=3e-6)
+    ext = torch.from_numpy(hd[0][0].T.astype(np.float32)).cuda().contiguous()
+    mean = m.bp_dns(zt, 0.7, ext)
+    np.testing.assert_allclose(mean.cpu().numpy(), mean_ref.T, rtol=3e-3, atol=3e-3 * q * 0.05)
+    assert m.status() == 0
