@@ -840,10 +840,11 @@ static int launch_gemm_tma(const ghm_model* m, int64_t B, int level, int n_nodes
 
 int ghm_wide_gemm_tc(const ghm_model* m, int64_t B, int level, int n_nodes, int down, const float* X, float* Y, cudaStream_t st) {
     const GhmDev& d = m->d;
-    const int N = d.QW;
-    if (N != 64 && N != 128 && N != 192 && N != 256) return GHM_EUNSUP;
-    if (n_nodes > 65535) return GHM_EUNSUP;
+    const int N = d.QW;                                        // a multiple of 32 in [32, 256]: UMMA M = 128 takes N % 16 == 0
     const int kind = m->gemm_mode;
+    if (N < 32 || N > 256 || (N % 32) != 0) return GHM_EUNSUP;
+    if (kind == GHM_GEMM_BF16 && (N % 64) != 0) return GHM_EUNSUP;    // BF16 stages 64-element (128-byte) K chunks
+    if (n_nodes > 65535) return GHM_EUNSUP;
     if (kind == GHM_GEMM_TF32) {
         const int rc = launch_gemm_tma(m, B, level, n_nodes, down, X, Y, st);
         if (rc != GHM_EUNSUP) return rc;
@@ -880,14 +881,15 @@ static int launch_fused(const ghm_model* m, int64_t B, int mode, int n_nodes, co
             (e[0] == 'c' && mode == LF_CLS))
             return GHM_EUNSUP;
     }
-    if (N != 64 && N != 128 && N != 192 && N != 256) return GHM_EUNSUP;
+    if (N < 32 || N > 256 || (N % 32) != 0) return GHM_EUNSUP;
     if (n_nodes > 65535) return GHM_EUNSUP;
     CUtensorMap mapW;
     if (!make_map(&mapW, (mode == LF_UP || mode == LF_CLS) ? d.Wup : d.Wdn, (uint64_t)d.n_mat * (uint64_t)N, N, N)) return GHM_EUNSUP;
     const int stage_bytes = TC_M * 128 + N * 128;
     int stages = std::min(4, N / 32);
     while (stages > 2 && (size_t)stages * stage_bytes + 1024 > 110 * 1024) --stages;     // two CTAs per SM
-    const size_t dyn = (size_t)stages * stage_bytes + 1024;
+    // the epilogue reuses the operand stages for its eight 32 x 32 transpose tiles
+    const size_t dyn = std::max((size_t)stages * stage_bytes, (size_t)FUSED_PROD_WARPS * 32 * EPI_PITCH * sizeof(float)) + 1024;
     dim3 grid((unsigned)((B + TC_M - 1) / TC_M), (unsigned)n_nodes);
     auto go = [&](auto kern) -> int {
         GHM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));

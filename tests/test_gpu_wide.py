@@ -177,3 +177,26 @@ def test_wide_tf32_fused_levels_per_edge_tables(ops):
     mean = m.bp_dns(zt, 0.7, ext)
     np.testing.assert_allclose(mean.cpu().numpy(), mean_ref.T, rtol=3e-3, atol=3e-3 * q * 0.05)
     assert m.status() == 0
+
+
+@pytest.mark.parametrize("L,s,q,B", [(3, 3, 20, 300), (2, 3, 32, 257), (3, 2, 96, 200), (2, 2, 150, 129), (2, 3, 224, 140)])
+def test_wide_tf32_every_multiple_of_32(ops, L, s, q, B):
+    """The TF32 tensor path takes every padded width QW = 32, 64, ..., 256 (UMMA M = 128 needs N % 16 == 0): q = 20 and 32
+    run as N = 32 -- the step right after the register-resident kernels (q <= 16)."""
+    from oracle import ghm_oracle as O
+    T, py, m = _model(ops, L, s, q, True, seed=31, p=0.3)
+    rng = np.random.RandomState(14)
+    vals = O.sample_tree(T, L, s, q, B, root=rng.randint(0, q, size=B), U=rng.rand(O.n_edges(L, s), B))
+    leaves = torch.from_numpy(vals[-1].T.copy()).cuda()
+    z = vals[-1] + rng.randn(s ** L, B)
+    zt = torch.from_numpy(z.T.astype(np.float32)).cuda().contiguous()
+    p32, h32 = m.bp_cls(leaves)
+    m.set_gemm_mode(m.GEMM_TF32)
+    ptc, htc = m.bp_cls(leaves)
+    meantc = m.bp_dns(zt, 1.0, h32)
+    torch.cuda.synchronize()
+    assert not torch.equal(ptc, p32), "TF32 mode produced bit-identical results: the tensor path did not run"
+    post, hd = O.bp_cls(T, vals[-1], L, s, q, py)
+    mean_ref = O.bp_dns(T, z, 1.0, L, s, q, ext=hd[0][0])[0]
+    np.testing.assert_allclose(ptc.cpu().numpy(), post.T, rtol=3e-3, atol=3e-6)
+    np.testing.assert_allclose(meantc.cpu().numpy(), mean_ref.T, rtol=3e-3, atol=3e-3 * q * 0.05)

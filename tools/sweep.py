@@ -43,7 +43,7 @@ def main():
             m = ops.GhmModel(T, L, s, q, p_y=np.ones(q) / q, device=dev)
             per_tree = (3 * n_nodes + 3 * nL) * max(q, 64) * 4 if q > 16 else 4 * n_nodes * q * 4 + 16 * nL
             B = int(max(1024, min(262144, (6 << 30) // per_tree)) // 256 * 256)
-            modes = ["f32"] + (["tf32", "bf16"] if q >= 64 else [])
+            modes = ["f32"] + (["tf32"] if q > 16 else []) + (["bf16"] if q >= 64 else [])
             for mode in modes:
                 m.set_gemm_mode({"f32": 0, "tf32": 1, "bf16": 2}[mode])
 
