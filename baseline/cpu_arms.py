@@ -222,7 +222,31 @@ def c5_pair(impl, B, seed, q=10):
     return 2 * B, time.perf_counter() - t0
 
 
-TASKS = {f.__name__: f for f in (c2_clip, c1_cdm, c1_dns, c3_sigma, c4_nwp, c4_nwp_guides, c5_q10, c5_q256, c5_pair)}
+def feed_cdm(impl, B, seed):
+    """Training-loop feed (training/train_CDNS.py:128): ConditionalDenoiseSampler([4,4],[3,3],p=.2).get_batch(B, guide=True)."""
+    q = 10
+    if impl == "reference":
+        s = _ref().ConditionalDenoiseSampler([4, 4], [3, 3], [_u(q), _u(q)], [0.2, 0.2], sigma=1)
+        np.random.seed(seed)
+        t0 = time.perf_counter()
+        s.get_batch(batch_size=B, guide=True)
+    else:
+        O = _port()
+        m = O.PairedModel([4, 4], [3, 3], [_u(q), _u(q)], [0.2, 0.2], q=q)
+        np.random.seed(seed)
+        t0 = time.perf_counter()
+        r = O.cdm_get_batch(m, B, sigma=1.0)
+        O.guides_cls(r["t_hd"], 4, 3)
+        O.guides_dns(r["hd"], r["qd"], r["bu"], 4, 3)
+    return 2 * B, time.perf_counter() - t0
+
+
+def feed_vlm(impl, B, seed):
+    """Training-loop feed (training/train_NWP.py:128): NextWordPredictSampler([4,4],[3,3],p=.2).get_batch(B, guide=True)."""
+    return _c4(impl, B, seed, True)
+
+
+TASKS = {f.__name__: f for f in (feed_cdm, feed_vlm, c2_clip, c1_cdm, c1_dns, c3_sigma, c4_nwp, c4_nwp_guides, c5_q10, c5_q256, c5_pair)}
 
 
 def _worker(args):

@@ -729,6 +729,30 @@ def config_blocks(dev, pool, cores, A, have_ref, hbm_peak):
         c5[tag]["gpu_over_cpu_ncore"] = c5[tag]["trees_per_s"] / base["trees_per_s"]
     c5["cpu_kind"] = base["impl"]
     out["C5"] = c5
+
+    # ---- training-loop feed: batch 128, guide=True, every iteration (train_CDNS.py:128, train_NWP.py:128) ----
+    from ghm_b200.feed import BatchPrefetcher
+    feed = {"workload": "sampler.get_batch(batch_size=128, guide=True) per training iteration: the reference calls it synchronously on "
+                        "the CPU; here feed.BatchPrefetcher keeps two batches in flight on a side stream (device tensors, no host "
+                        "synchronisation) and the consumer waits on an event", "batch": 128}
+    for name, cls, task in (("cdm", G.ConditionalDenoiseSampler, "feed_cdm"), ("vlm", G.NextWordPredictSampler, "feed_vlm")):
+        smp = cls(N_LAYERS, N_CHILDS, [u, u], P_FLIPS, device=dev, rng="philox", seed=91)
+        pf = BatchPrefetcher(smp, batch_size=128, guide=True, depth=2)
+        for _ in range(20):
+            next(pf)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nb = 200
+        for _ in range(nb):
+            next(pf)
+        torch.cuda.synchronize()
+        us = 1e6 * (time.perf_counter() - t0) / nb
+        sync_ms = _wall_ms(lambda i: smp.get_batch(batch_size=128, guide=True, device=dev), 50)
+        cpu = A.fan_out(pool, 1, task, "reference" if have_ref else "port", 128, 5, reps=8)
+        feed[name] = {"prefetched_us_per_batch": us, "synchronous_get_batch_us": 1e3 * sync_ms,
+                      "cpu_1core_us_per_batch": 1e6 * cpu["seconds"] / cpu["calls_per_core"], "cpu_kind": cpu["impl"]}
+        del pf, smp
+    out["feed"] = feed
     return out
 
 
