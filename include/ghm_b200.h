@@ -125,6 +125,16 @@ GHM_API int ghm_sample_blocked(const ghm_model_t* m, int64_t B, int64_t blk_len,
                        int64_t* root_out, void* leaves_out, int leaf_dtype, float* post_out, float* root_hd_out,
                        void* stream);
 
+/* ClipSampler.get_Bayes (:786-817) as ONE device-side call: sample both modalities in the block layout (:758-760) with
+ * the root-posterior BP fused (:767-768) -- the image launch on `side_stream`, forked from and joined to `stream` --
+ * and accumulate the symmetric K-way contrastive loss (:794-817) of pairs [pair_lo, pair_hi) into `sums` (device
+ * double[3]: sum, sum of squares, count).  All buffers are the caller's ((pair_hi - pair_lo) * (K + 1) trees per
+ * modality; t_root / t_leaves / i_leaves may be null); nothing is copied to the host, nothing synchronises.  A rank's
+ * shard draws exactly the trees the whole evaluation draws for those pairs (ghm_sample_blocked).  Philox mode. */
+GHM_API int ghm_clip_bayes(const ghm_model_t* text, const ghm_model_t* image, int64_t n, int K, int64_t pair_lo,
+                   int64_t pair_hi, uint64_t seed, uint64_t tree_offset, int64_t* t_root, void* t_leaves, void* i_leaves,
+                   int leaf_dtype, float* t_pp, float* i_pp, double* sums, void* stream, void* side_stream);
+
 GHM_API int ghm_sample_paired(const ghm_model_t* m, int64_t B, int64_t n_shared, uint64_t root_seed, uint64_t seed,
                       uint64_t tree_offset, int64_t* root_out, void* leaves_out, int leaf_dtype,
                       float* post_out, float* root_hd_out, void* stream);

@@ -74,8 +74,15 @@ struct ghm_model {
     float* h_TlinT;
     cudaEvent_t upload_done;   // fences the last H2D table upload ONLY (ghm_model_update waits on it before rewriting h_slab)
     cudaEvent_t order_ev;      // plain stream-ordering event of the ghm_host_* entry points
-    void* slab;          // single device allocation holding every table
+    void* slab;          // device allocation holding every table (the ACTIVE one of slabs[])
     size_t slab_bytes;
+    // ghm_model_update double-buffers the tables: update u fills (h_slabs / slabs)[u & 1] and re-points `d`, so kernels
+    // launched before it keep reading the other slab (GhmDev travels by value) and consecutive evaluations of a p_flip
+    // sweep can overlap on different streams.  slabs[0] is the slab of ghm_model_create and owns the sticky status word.
+    void* slabs[2];
+    void* h_slabs[2];
+    cudaEvent_t upload_evs[2];
+    int active;
     cudaStream_t stream; // internal stream for ghm_host_* entry points
     // host scratch for ghm_host_* (lazily sized)
     void* h_scratch; size_t h_scratch_bytes;

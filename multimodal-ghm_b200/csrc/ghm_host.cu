@@ -20,6 +20,52 @@ static int ensure_dscratch(ghm_model* m, size_t bytes) {
 
 static size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 
+// ------------------------------------------------------------------------------------------------
+// ghm_clip_bayes: the device-side form of the same evaluation -- every buffer is the caller's, nothing is copied to the
+// host and nothing synchronises.  One call enqueues: image sampling + fused BP on `side_stream` (forked from `stream`
+// through the image model's ordering event), text sampling + fused BP on `stream`, the join, and the contrastive
+// reduction accumulated into `sums`.  Pairs [pair_lo, pair_hi) of the n-pair block layout are evaluated (a rank's
+// shard; the whole evaluation is pair_lo = 0, pair_hi = n): ghm_sample_blocked gives them the global Philox indices
+// of the unsharded launch.  Replaces five Python-level calls of the facade's get_Bayes with one.
+// ------------------------------------------------------------------------------------------------
+extern "C" int ghm_clip_bayes(const ghm_model_t* text_c, const ghm_model_t* image_c, int64_t n, int K, int64_t pair_lo,
+                              int64_t pair_hi, uint64_t seed, uint64_t tree_offset, int64_t* t_root, void* t_leaves,
+                              void* i_leaves, int leaf_dtype, float* t_pp, float* i_pp, double* sums, void* stream,
+                              void* side_stream) {
+    ghm_model* text = const_cast<ghm_model*>(text_c);
+    ghm_model* image = const_cast<ghm_model*>(image_c);
+    if (!text || !image || !t_pp || !i_pp || !sums) return ghm_fail(GHM_EINVAL, "ghm_clip_bayes: null argument");
+    if (text->d.q != image->d.q) return ghm_fail(GHM_EINVAL, "text and image models disagree on q");
+    if (text->device != image->device) return ghm_fail(GHM_EINVAL, "text and image models live on different devices");
+    if (n <= 0 || K < 2 || pair_lo < 0 || pair_hi > n || pair_lo > pair_hi)
+        return ghm_fail(GHM_EINVAL, "ghm_clip_bayes: bad n=%lld K=%d pairs [%lld, %lld)", (long long)n, K, (long long)pair_lo,
+                        (long long)pair_hi);
+    const int64_t nl = pair_hi - pair_lo;
+    if (nl == 0) return GHM_OK;
+    GhmDeviceGuard guard(text->device);
+    cudaStream_t st = (cudaStream_t)stream, st2 = (cudaStream_t)side_stream;
+    const int64_t Bl = nl * (K + 1);
+    const uint64_t iseed = seed ^ GHM_IMAGE_SEED_XOR;
+    int rc;
+    if (st2 && st2 != st) {
+        GHM_CUDA_TRY(cudaEventRecord(image->order_ev, st));            // fork: the side stream starts after what `stream` holds
+        GHM_CUDA_TRY(cudaStreamWaitEvent(st2, image->order_ev, 0));
+    } else {
+        st2 = st;
+    }
+    rc = ghm_sample_blocked(image, Bl, nl, n, GHM_ROOT_SHARED, 2 * nl, nullptr, seed, iseed, tree_offset + (uint64_t)pair_lo,
+                            nullptr, i_leaves, leaf_dtype, i_pp, nullptr, st2);
+    if (rc) return rc;
+    rc = ghm_sample_blocked(text, Bl, nl, n, GHM_ROOT_UNIFORM, 0, nullptr, 0, seed, tree_offset + (uint64_t)pair_lo, t_root,
+                            t_leaves, leaf_dtype, t_pp, nullptr, st);
+    if (rc) return rc;
+    if (st2 != st) {
+        GHM_CUDA_TRY(cudaEventRecord(text->order_ev, st2));             // join
+        GHM_CUDA_TRY(cudaStreamWaitEvent(st, text->order_ev, 0));
+    }
+    return ghm_risk_clip(t_pp, i_pp, nl, K, text->d.q, 0, nl, sums, st);
+}
+
 extern "C" int ghm_host_clip_bayes(const ghm_model_t* text_c, const ghm_model_t* image_c, int64_t n, int K,
                                    uint64_t seed, uint64_t tree_offset, double* sums_host, void* t_leaves_host,
                                    void* i_leaves_host, int leaf_dtype, float* t_pp_host, float* i_pp_host) {

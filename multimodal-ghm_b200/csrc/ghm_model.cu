@@ -154,6 +154,30 @@ static int derive_tables(const GhmDev& d, const double* T_host, const double* p_
     return GHM_OK;
 }
 
+// make slab `which` the active one: device table pointers of `d`, host sources of the constant-bank kernel parameters
+static void point_tables(ghm_model* m, int which) {
+    GhmDev& d = m->d;
+    const SlabLayout o = slab_layout(d);
+    char* base = (char*)m->slabs[which];
+    d.Tlin = (const float*)(base + o.Tlin);
+    d.TlinT = (const float*)(base + o.TlinT);
+    d.TlogT = (const float*)(base + o.TlogT);
+    d.TTp = (const float*)(base + o.TTp);
+    d.Wup = (const float*)(base + o.Wup);
+    d.Wdn = (const float*)(base + o.Wdn);
+    d.alias = (const uint32_t*)(base + o.alias);
+    d.cdfd = (const double*)(base + o.cdfd);
+    d.py = (const float*)(base + o.py);
+    d.root_cdfu_prior = (const uint32_t*)(base + o.rcp);
+    d.root_cdfu_unif = (const uint32_t*)(base + o.rcu);
+    char* hb = (char*)m->h_slabs[which];
+    m->h_TTp = (float*)(hb + o.TTp);
+    m->h_Tlin = (float*)(hb + o.Tlin);
+    m->h_TlinT = (float*)(hb + o.TlinT);
+    m->slab = m->slabs[which]; m->h_slab = m->h_slabs[which]; m->upload_done = m->upload_evs[which];
+    m->active = which;
+}
+
 extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, const double* T_host,
                                 const double* p_y_host, int device) {
     if (!out || !T_host) return ghm_fail(GHM_EINVAL, "ghm_model_create: null argument");
@@ -220,22 +244,10 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     MC_TRY(cudaEventCreateWithFlags(&m->order_ev, cudaEventDisableTiming));
     MC_TRY(cudaSetDevice(prev));
 #undef MC_TRY
-    char* base = (char*)m->slab;
-    d.Tlin = (const float*)(base + o.Tlin);
-    d.TlinT = (const float*)(base + o.TlinT);
-    d.TlogT = (const float*)(base + o.TlogT);
-    d.TTp = (const float*)(base + o.TTp);
-    d.Wup = (const float*)(base + o.Wup);
-    d.Wdn = (const float*)(base + o.Wdn);
-    d.alias = (const uint32_t*)(base + o.alias);
-    d.cdfd = (const double*)(base + o.cdfd);
-    d.py = (const float*)(base + o.py);
-    d.root_cdfu_prior = (const uint32_t*)(base + o.rcp);
-    d.root_cdfu_unif = (const uint32_t*)(base + o.rcu);
-    d.status = (int*)(base + o.status);
-    m->h_TTp = (float*)((char*)m->h_slab + o.TTp);
-    m->h_Tlin = (float*)((char*)m->h_slab + o.Tlin);
-    m->h_TlinT = (float*)((char*)m->h_slab + o.TlinT);
+    m->slabs[0] = m->slab; m->h_slabs[0] = m->h_slab; m->upload_evs[0] = m->upload_done;
+    m->slabs[1] = nullptr; m->h_slabs[1] = nullptr; m->upload_evs[1] = nullptr;
+    d.status = (int*)((char*)m->slab + o.status);              // the sticky status word stays in slab 0 for the model's lifetime
+    point_tables(m, 0);
     rc = ghm_guides_init(m);
     if (rc) { ghm_model_destroy(m); return rc; }
     *out = m;
@@ -244,8 +256,10 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
 
 // New tables for an existing model of the same shape (the p_flip sweeps of figures/eval-*-ood.py build a new
 // sampler per p, :76-79): derive on the host, one H2D copy of the slab from pinned memory, enqueued on `stream`.
-// Kernels enqueued on `stream` AFTER this call see the new tables; the caller must not have kernels of this model
-// in flight on OTHER streams.  The sticky status word is preserved.
+// Kernels launched AFTER this call (on `stream`, or on a stream that waits for it) see the new tables.  The tables are
+// double buffered: kernels launched BEFORE this call keep reading the previous slab and may still be running on other
+// streams; they must have finished before the update AFTER this one starts to overwrite that slab (same stream: by
+// stream order; other streams: the caller makes `stream` wait for them).  The sticky status word is preserved.
 extern "C" int ghm_model_update(ghm_model_t* m, const double* T_host, const double* p_y_host, void* stream) {
     if (!m || !T_host) return ghm_fail(GHM_EINVAL, "ghm_model_update: null argument");
     int prev = 0;
@@ -254,12 +268,19 @@ extern "C" int ghm_model_update(ghm_model_t* m, const double* T_host, const doub
     struct Restore { int p, dev; ~Restore() { if (p != dev) cudaSetDevice(p); } } restore{prev, m->device};
     int vrc = validate_tables(m->d, T_host, p_y_host);           // before anything is rewritten
     if (vrc) return vrc;
-    GHM_CUDA_TRY(cudaEventSynchronize(m->upload_done));          // the previous upload has consumed the pinned slab
     const SlabLayout o = slab_layout(m->d);
-    int rc = derive_tables(m->d, T_host, p_y_host, (char*)m->h_slab);
+    const int next = 1 - m->active;
+    if (!m->slabs[next]) {                                       // first update: the second buffer pair
+        GHM_CUDA_TRY(cudaMallocHost(&m->h_slabs[next], o.bytes));
+        GHM_CUDA_TRY(cudaMalloc(&m->slabs[next], o.bytes));
+        GHM_CUDA_TRY(cudaEventCreateWithFlags(&m->upload_evs[next], cudaEventDisableTiming));
+    }
+    GHM_CUDA_TRY(cudaEventSynchronize(m->upload_evs[next]));     // the upload that last used this pinned buffer has consumed it
+    int rc = derive_tables(m->d, T_host, p_y_host, (char*)m->h_slabs[next]);
     if (rc) return rc;
-    GHM_CUDA_TRY(cudaMemcpyAsync(m->slab, m->h_slab, o.status, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    GHM_CUDA_TRY(cudaEventRecord(m->upload_done, (cudaStream_t)stream));
+    GHM_CUDA_TRY(cudaMemcpyAsync(m->slabs[next], m->h_slabs[next], o.status, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    GHM_CUDA_TRY(cudaEventRecord(m->upload_evs[next], (cudaStream_t)stream));
+    point_tables(m, next);
     return GHM_OK;
 }
 
@@ -279,11 +300,14 @@ extern "C" int ghm_model_destroy(ghm_model_t* m) {
     cudaGetDevice(&prev);
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamDestroy(m->stream);
-    if (m->upload_done) cudaEventDestroy(m->upload_done);
+    if (!m->slabs[0]) { m->slabs[0] = m->slab; m->h_slabs[0] = m->h_slab; m->upload_evs[0] = m->upload_done; }   // create() failed early
+    for (int i = 0; i < 2; ++i) {
+        if (m->upload_evs[i]) cudaEventDestroy(m->upload_evs[i]);
+        if (m->slabs[i]) cudaFree(m->slabs[i]);
+        if (m->h_slabs[i]) cudaFreeHost(m->h_slabs[i]);
+    }
     if (m->order_ev) cudaEventDestroy(m->order_ev);
-    if (m->slab) cudaFree(m->slab);
     if (m->guide_tab) cudaFree(m->guide_tab);
-    if (m->h_slab) cudaFreeHost(m->h_slab);
     if (m->d_scratch) cudaFree(m->d_scratch);
     if (m->h_scratch) cudaFreeHost(m->h_scratch);
     cudaSetDevice(prev);

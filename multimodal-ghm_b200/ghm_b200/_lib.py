@@ -29,6 +29,8 @@ SIGNATURES = {
     "ghm_model_set_gemm_mode": (c_int, [c_vp, c_int]),
     "ghm_bp_cls_workspace_bytes": (c_i64, [c_vp, c_i64]),
     "ghm_sample_paired": (c_int, [c_vp, c_i64, c_i64, c_u64, c_u64, c_u64, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+    "ghm_clip_bayes": (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_i64, c_u64, c_u64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp,
+                               c_vp, c_vp]),
     "ghm_sample_blocked": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_i64, c_vp, c_u64, c_u64, c_u64, c_vp, c_vp, c_int, c_vp,
                                    c_vp, c_vp]),
     "ghm_bp_cls": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),

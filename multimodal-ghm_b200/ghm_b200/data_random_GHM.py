@@ -22,6 +22,7 @@ Deliberate deviations, each mirrored from SURVEY.md section 8 / Appendix A:
   * ``Node`` objects exist for ``root_node`` / ``leaves_nodes`` only (no per-node message graph).
   * ``BP_dummy_NWP`` / ``BP_NWP`` (dead code upstream, :223-334) raise NotImplementedError.
 """
+import collections
 import weakref
 
 import numpy as np
@@ -479,11 +480,35 @@ class _SamplerBase:
         self.rng, self.seed = rng, int(seed)
         self.tree_offset = 0          # global index of the next Philox tree (explicit, resumable RNG state)
 
+    def _eval_stream(self):
+        """Lazy risk evaluations alternate between two internal streams, so that evaluation k+1 (after a table swap: the
+        model tables are double buffered, ``ghm_model_update``) starts while the tail of evaluation k drains -- the same
+        overlap ``bench.py``'s device-resident loop gets from its two pipelines."""
+        sts = getattr(self, "_eval_streams", None)
+        if sts is None:
+            sts = self._eval_streams = [torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)]
+            self._eval_turn = 0
+            self._lazy_events = collections.deque(maxlen=4)       # (event, table version the evaluation read)
+        self._eval_turn ^= 1
+        return sts[self._eval_turn]
+
+    def _fence_tables(self):
+        """Called before the model tables are swapped to version v+1, which overwrites the slab of version v-1 (double
+        buffering): the current stream waits for every lazy evaluation that read version v-1 or older (normally long
+        complete), then the version counter advances."""
+        v = getattr(self, "_table_version", 0)
+        for ev, ver in getattr(self, "_lazy_events", ()):
+            if ver <= v - 1:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+        self._table_version = v + 1
+
     def _side_stream(self):
-        st = getattr(self, "_side", None)
-        if st is None:
-            st = self._side = torch.cuda.Stream(device=self.device)
-        return st
+        """Stream of the image-side launch; lazy evaluations get one per evaluation stream so that they do not queue behind
+        each other."""
+        sides = getattr(self, "_sides", None)
+        if sides is None:
+            sides = self._sides = [torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)]
+        return sides[getattr(self, "_eval_turn", 0)]
 
     def _advance(self, n):
         off = self.tree_offset
@@ -557,6 +582,7 @@ class DoubleSampler(_SamplerBase):
         else:
             t_tr, i_tr = transitions
         self.t_transition, self.i_transition = t_tr, i_tr
+        self._fence_tables()
         self.t_model.update(t_tr, self.p_ys[0])
         self.i_model.update(i_tr, self.p_ys[1])
         return self
@@ -771,9 +797,6 @@ class ClipSampler(DoubleSampler):
         ops.sample_blocked_into(self.t_model, Bl, nl, n, ops.ROOT_UNIFORM, 0, None, 0, self.seed, off + pair_lo,
                                 t["root"], t["leaves"], t["post"], None)
         cur.wait_stream(side)
-        for x in (i["root"], i["leaves"], i["post"]):
-            if x is not None:
-                x.record_stream(side)
         return {"t": t, "i": i, "n_local": nl}
 
     def get_batch(self, device="cpu", batch_size=128, guide=False, async_=False):
@@ -805,19 +828,54 @@ class ClipSampler(DoubleSampler):
             lo, hi = shard_range(n_eval, rank, world)
         else:
             lo, hi = 0, n_eval
-        r = self._sample_layout(n_eval, want_leaves=keep_batch, want_post=True, pair_lo=lo, pair_hi=hi)
-        self.last_batch = r if keep_batch else None
-        nl = r["n_local"]
-        sums = ops.new_sums(self.device)
-        if nl > 0:
-            ops.risk_clip(r["t"]["post"], r["i"]["post"], nl, K, q, sums=sums)
-        if distributed:
-            all_reduce_sums(sums, group)
-
         def finish(s):
             mean, se = mean_se_from_sums(s)
             return np.float64(mean), np.float64(se)
-        return LazyRisk(sums, finish) if lazy else finish(sums)
+
+        def evaluate():
+            if self.rng == "philox" and q <= 16:
+                # ONE library call (ghm_clip_bayes): both sampling launches with the BP fused, fork / join of the side
+                # stream and the contrastive reduction -- the Python-level sequence below costs 0.1 ms more per evaluation
+                dev, nl = self.device, hi - lo
+                Bl = nl * (K + 1)
+                off = self._advance(n_eval * (K + 1))
+                sums = ops.new_sums(dev)
+                t = {"root": torch.empty(Bl, dtype=torch.int64, device=dev), "leaves": None,
+                     "post": torch.empty((Bl, q), dtype=torch.float32, device=dev)}
+                i = {"root": None, "leaves": None, "post": torch.empty((Bl, q), dtype=torch.float32, device=dev)}
+                if keep_batch:
+                    t["leaves"] = torch.empty((Bl, self.t_model.n_leaves), dtype=torch.int64, device=dev)
+                    i["leaves"] = torch.empty((Bl, self.i_model.n_leaves), dtype=torch.int64, device=dev)
+                side = self._side_stream()
+                ops.clip_bayes_into(self.t_model, self.i_model, n_eval, K, lo, hi, self.seed, off, t["root"], t["leaves"],
+                                    i["leaves"], t["post"], i["post"], sums, side_stream=side)
+                # (the call joins `side` back into the current stream, so the allocator's stream-ordered reuse is safe)
+                self.last_batch = {"t": t, "i": i, "n_local": nl} if keep_batch else None
+            else:
+                r = self._sample_layout(n_eval, want_leaves=keep_batch, want_post=True, pair_lo=lo, pair_hi=hi)
+                self.last_batch = r if keep_batch else None
+                nl = r["n_local"]
+                sums = ops.new_sums(self.device)
+                if nl > 0:
+                    ops.risk_clip(r["t"]["post"], r["i"]["post"], nl, K, q, sums=sums)
+            if distributed:
+                all_reduce_sums(sums, group)
+            return sums
+        if not (lazy and self.rng == "philox"):
+            sums = evaluate()
+            return LazyRisk(sums, finish) if lazy else finish(sums)
+        # lazy: the whole evaluation runs on one of two internal streams (ordered after everything already enqueued on the
+        # caller's stream, e.g. a table upload); `last_batch` and the result are valid once the handle's event has completed
+        cur = torch.cuda.current_stream(self.device)
+        ev_stream = self._eval_stream()
+        ev_stream.wait_stream(cur)
+        with torch.cuda.stream(ev_stream):
+            sums = evaluate()
+            handle = LazyRisk(sums, finish)
+        if len(self._lazy_events) == self._lazy_events.maxlen:
+            self._lazy_events[0][0].synchronize()            # at most four evaluations in flight: the fence above stays exact
+        self._lazy_events.append((handle._ev, getattr(self, "_table_version", 0)))
+        return handle
 
 
 class ConditionalDenoiseSampler(DoubleSampler):

@@ -331,6 +331,18 @@ def sample_blocked_into(model, batch, blk_len, blk_stride, root_mode, n_given, r
                                             _ptr(post_out), _ptr(root_hd_out), _stream()))
 
 
+def clip_bayes_into(text, image, n, K, pair_lo, pair_hi, seed, tree_offset, t_root, t_leaves, i_leaves, t_pp, i_pp, sums,
+                    side_stream=None):
+    """ghm_clip_bayes: sample both modalities (+ fused BP) and accumulate the contrastive risk of pairs [pair_lo, pair_hi)
+    into ``sums`` with ONE library call; the image launch runs on ``side_stream`` (a torch.cuda.Stream) when given."""
+    code = _leaf_code(t_leaves) if t_leaves is not None else LEAF_I64
+    with _on(text.device):
+        check(text._lib.ghm_clip_bayes(text._h, image._h, int(n), int(K), int(pair_lo), int(pair_hi), seed, tree_offset,
+                                       _ptr(t_root), _ptr(t_leaves), _ptr(i_leaves), code, _ptr(t_pp), _ptr(i_pp), _ptr(sums),
+                                       _stream(), C.c_void_p(side_stream.cuda_stream if side_stream is not None else 0)))
+    return sums
+
+
 def new_sums(device):
     """Zeroed {sum, sum of squares, count} accumulator (float64[3]) for the risk kernels."""
     return torch.zeros(3, dtype=torch.float64, device=device)
