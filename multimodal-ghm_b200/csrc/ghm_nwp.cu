@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(NWP_NT) k_nwp_pos(const GhmDev d, const NwpArg
         for (int i = tid; i < tab_words; i += NT) s1[i] = d.Tlin[i];
         Tlin = s1;
     }
-    float* HD = reinterpret_cast<float*>(smem + off); off += (size_t)L * Q * NT * 4;   // [L][Q][NT] (depth 1..L-1 used)
+    const int nlv = L > 1 ? L - 1 : 1;                       // path nodes at depth 1 .. L-1: one slot each (a fourth, unused slot
+    float* HD = reinterpret_cast<float*>(smem + off); off += (size_t)nlv * Q * NT * 4;   // cost 10 KB: 4 instead of 6 CTAs/SM)
     float* QD = reinterpret_cast<float*>(smem + off);                                    // [L][Q][NT]
     if (SMEM_TAB) __syncthreads();
 
@@ -169,8 +170,8 @@ __global__ void __launch_bounds__(NWP_NT) k_nwp_pos(const GhmDev d, const NwpArg
         const int mi = d.mat_off[l] + (d.ti ? pc : pidx);
         ghm_matvec<Q>(Tlin + (size_t)mi * Q * Q, h, m);
         ghm_normalize<Q>(m);
-        float* Hl = HD + (size_t)l * Q * NT + tid;
-        float* Ql = QD + (size_t)l * Q * NT + tid;
+        float* Hl = HD + (size_t)(l - 1) * Q * NT + tid;
+        float* Ql = QD + (size_t)(l - 1) * Q * NT + tid;
 #pragma unroll
         for (int k = 0; k < Q; ++k) { Hl[k * NT] = h[k]; Ql[k * NT] = m[k]; }
         if (GUIDE) {
@@ -219,8 +220,8 @@ __global__ void __launch_bounds__(NWP_NT) k_nwp_pos(const GhmDev d, const NwpArg
         const int mi = d.mat_off[l] + (d.ti ? cg : g);
         float w[Q], tt[Q];
         if (g == a_l) {                                         // shared ancestor: cavity update (l <= L-1 here)
-            const float* Hl = HD + (size_t)l * Q * NT + tid;
-            const float* Ql = QD + (size_t)l * Q * NT + tid;
+            const float* Hl = HD + (size_t)(l - 1) * Q * NT + tid;
+            const float* Ql = QD + (size_t)(l - 1) * Q * NT + tid;
 #pragma unroll
             for (int k = 0; k < Q; ++k) { const float qv = Ql[k * NT]; w[k] = qv > 0.f ? __fdividef(bel[k], qv) : 0.f; }
             ghm_matvec_t<Q>(Tlin + (size_t)mi * Q * Q, w, tt);
@@ -540,7 +541,7 @@ static int launch_nwp(const ghm_model* m, const NwpArgs& a, cudaStream_t st) {
         GHM_CHECK_LAUNCH();
     }
     const size_t tab_bytes = (size_t)d.n_mat * Q * Q * 4;
-    size_t dyn = (size_t)2 * d.L * Q * NWP_NT * 4;
+    size_t dyn = (size_t)2 * (d.L > 1 ? d.L - 1 : 1) * Q * NWP_NT * 4;
     const bool smem_tab = tab_bytes + dyn <= 100 * 1024;
     if (smem_tab) dyn += tab_bytes;
     if (dyn > 200 * 1024)
