@@ -61,7 +61,7 @@ KTREE = {
     "dram_bytes_per_tree": 518.8,          # 169.92 MB written + 0.09 MB read per launch (below the 696 B/tree algorithmic
                                            # figure: the tail of the leaves is still in the 126 MB L2 when the kernel ends)
     "warp_inst_per_tree": 106626560 / 327680,
-    "share": 0.955,
+    "share": 0.96,                         # of the GPU time in the serialised ncu launch list of this script (profiles/r02_launches_bench_clip.csv)
     "note": "no single unit is the wall: issue slots 0.60, FMA-heavy pipe 0.54 (FFMA2 2.1 clk, Philox IMAD.WIDE 4.3 clk per warp "
             "instruction), ALU pipe 0.35, shared-memory pipe 0.52 at 4 warps per scheduler (123 registers, 54 KB); a fifth CTA "
             "per SM measured 7 % SLOWER; the HBM fraction is reported, not padded; see roofline.secondary and DESIGN.md 3.1",
@@ -528,7 +528,7 @@ def strong_scaling(args, rank, world, dev, barrier):
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / reps, h
 
-        reps = 3 if q <= 16 else 1
+        reps = 10 if q <= 16 else 2                          # back-to-back evaluations (lazy handles): steady-state time per evaluation
         if os.environ.get("GHM_BENCH_DEBUG"):
             st0 = torch.cuda.memory_stats(dev)
         ms, h = timed(world > 1, reps)
