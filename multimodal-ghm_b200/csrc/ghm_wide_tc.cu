@@ -640,8 +640,11 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_wide_fused(const __grid_const
         }
         for (int kc = 0; kc < nchunks; ++kc) {
             const int st = kc % stages;
-            if (kc >= stages) mbar_wait(&empty_bar[st], ((kc / stages) - 1) & 1);
             unsigned char* At = tiles + (size_t)st * stage_bytes;
+            // The chunk's global loads are issued BEFORE waiting for its stage to be free: they only need registers, and their
+            // latency then overlaps the MMAs that still read the stage (2.72 -> 2.39 ms per BP_DNS at q = 256).  A second
+            // register buffer that fetches chunk kc+1 ahead of chunk kc's conversion costs 127 registers x 320 threads = one
+            // CTA per SM instead of two and measured 2.77 ms.
             float4 pbv[4], puv[4];
             if (MODE == LF_CLS) {                                        // gathered rows: pbv = row of child 0 (x child 1), puv = child 2
 #pragma unroll
@@ -662,6 +665,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_wide_fused(const __grid_const
                     puv[i] = __ldg(reinterpret_cast<const float4*>(a.U + ((int64_t)node * B + bc) * N + kc * 32) + pc);
                 }
             }
+            if (kc >= stages) mbar_wait(&empty_bar[st], ((kc / stages) - 1) & 1);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int rl = 16 * half + 4 * i + (lane >> 3);          // row within the quarter
