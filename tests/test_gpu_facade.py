@@ -434,3 +434,49 @@ def test_bayes_checkpoint_key(G, kat, tmp_path):
     assert set(ckpt) >= {"iter", "loss_history", "ploss_history", "bayes"} and ckpt["iter"] == 7
     assert float(ckpt["bayes"]) == pytest.approx(kat["clip-risk.json"]["Bayes"][9], rel=1e-5)
     assert float(ckpt["loss_history"][-100:].mean()) == 1.0 and float(bayes) == float(ckpt["bayes"]) and std > 0
+
+
+def test_lazy_sweep_over_double_buffered_tables_equals_synchronous(G):
+    """The e2e pattern of bench.py: per grid point new tables (reparameterize -> ghm_model_update, double buffered) and a
+    lazy get_Bayes on one of two alternating streams, results read two calls late.  Every result must equal the
+    synchronous evaluation of the same grid point (same Philox trees, same tables: 1e-12), also when the same
+    tables are swapped in twice in a row and when evaluations are issued without a swap in between."""
+    import torch
+    n = 6000
+    grid = [0.04, 0.1, 0.16, 0.22, 0.28, 0.34, 0.1, 0.1, 0.4]
+    ref = []
+    s1 = G.ClipSampler([4, 4], [3, 3], [u10, u10], [.2, .2], rng="philox", seed=11)
+    for p in grid:
+        s1.reparameterize([p, p])
+        s1.tree_offset = 0
+        ref.append(s1.get_Bayes(n_eval=n, keep_batch=True))
+    s2 = G.ClipSampler([4, 4], [3, 3], [u10, u10], [.2, .2], rng="philox", seed=11)
+    pend, got = [], []
+    for k, p in enumerate(grid):
+        s2.reparameterize([p, p])
+        if k == 4:
+            s2.reparameterize([p, p])                       # two swaps in a row: the fence must still protect evaluation k-1
+        s2.tree_offset = 0
+        pend.append(s2.get_Bayes(n_eval=n, keep_batch=True, lazy=True))
+        if k == 6:                                          # a second evaluation of the same tables, no swap in between
+            s2.tree_offset = 0
+            extra = s2.get_Bayes(n_eval=n, lazy=True)
+        if len(pend) > 2:
+            got.append(pend.pop(0).result())
+    got += [h.result() for h in pend]
+    torch.cuda.synchronize()
+    # (the float64 atomics of the risk reduction complete in a different order from run to run: 1e-12, not bit equality)
+    for g, r in zip(got, ref):
+        assert tuple(map(float, g)) == pytest.approx(tuple(map(float, r)), rel=1e-12)
+    assert len(got) == len(ref)
+    assert tuple(map(float, extra.result())) == pytest.approx(tuple(map(float, ref[6])), rel=1e-12)
+    # the device-side one-call evaluation equals the Python-level sequence (sample both modalities + risk_clip)
+    from ghm_b200 import ops
+    s3 = G.ClipSampler([4, 4], [3, 3], [u10, u10], [.3, .3], rng="philox", seed=12)
+    r = s3._sample_layout(n, want_leaves=True, want_post=True)
+    a = ops.risk_clip(r["t"]["post"], r["i"]["post"], n, 4, 10)
+    s3.tree_offset = 0
+    h = s3.get_Bayes(n_eval=n, keep_batch=True, lazy=True)
+    h.result()
+    assert torch.equal(s3.last_batch["t"]["leaves"], r["t"]["leaves"]) and torch.equal(s3.last_batch["i"]["leaves"], r["i"]["leaves"])
+    assert h.sums() == pytest.approx([float(x) for x in a.tolist()], rel=1e-12)
