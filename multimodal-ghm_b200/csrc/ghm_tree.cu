@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(PAR_NT) k_sample_parity(const GhmDev d, const 
 }
 
 #ifdef GHM_TREE_PROBE   // development aid: compile one instantiation only (nvcc -DGHM_TREE_PROBE=2 -cubin)
-template __global__ void k_tree_fast<10, 3, MODE_PHILOX, true, 1536>(
+template __global__ void k_tree_fast<10, 3, MODE_PHILOX, true, 1536, false>(
     const __grid_constant__ GhmDev, const __grid_constant__ TreeArgs, const __grid_constant__ TabParam<1536>);
 #endif
 
@@ -105,7 +105,9 @@ static int sample_common(const ghm_model_t* m, int64_t B, int root_mode, int64_t
     a.B = B; a.root_mode = root_mode; a.n_given = n_given; a.root_in = root_in; a.root_seed = root_seed; a.U = U;
     a.seed = seed;
     a.tree_offset = tree_offset;
-    a.blk_len = blk_len; a.blk_stride = blk_stride;
+    if (blk_len > 0 && (B >= (1ll << 32) || blk_len >= (1ll << 32)))
+        return ghm_fail(GHM_EUNSUP, "ghm_sample_blocked: batches of 2^32 trees or more are not supported");
+    a.blk_len = (uint32_t)blk_len; a.blk_extra = (uint64_t)(blk_stride - blk_len);
     a.root_out = root_out; a.leaves = leaves_out; a.leaf_dtype = leaf_dtype; a.post = post_out; a.root_hd = root_hd_out;
     const bool bp = post_out || root_hd_out;
     if (bp && m->d.QW)

@@ -52,7 +52,8 @@ struct TreeArgs {
     uint64_t root_seed;    // GHM_ROOT_SHARED: Philox key of the roots of trees [0, n_given) (the partner modality's seed)
     const double* U;
     uint64_t seed, tree_offset;
-    int64_t blk_len, blk_stride;   // blk_len > 0: local tree b has global Philox index tree_offset + (b / blk_len) * blk_stride + b % blk_len
+    uint32_t blk_len;              // blk_len > 0 (ghm_sample_blocked, B < 2^32): local tree b has the global Philox index
+    uint64_t blk_extra;            //   tree_offset + b + (b / blk_len) * blk_extra,  blk_extra = blk_stride - blk_len
     int64_t* root_out;
     void* leaves;          // output (sampling modes) or input (MODE_GIVEN); may be null when sampling
     int leaf_dtype;
@@ -261,7 +262,8 @@ k_tree2(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a, co
         bt[t] = warp_tree0 + 32 * t + lane;
         active[t] = bt[t] < a.B;
         const int64_t bc = active[t] ? bt[t] : a.B - 1;          // tail threads shadow the last tree and never write
-        tree[t] = a.tree_offset + (uint64_t)(a.blk_len > 0 ? (bc / a.blk_len) * a.blk_stride + bc % a.blk_len : bc);
+        tree[t] = a.tree_offset + (uint64_t)bc;
+        if (a.blk_len) tree[t] += (uint64_t)((uint32_t)bc / a.blk_len) * a.blk_extra;
         srow[t] = (32 * t + lane) * a.stage_stride;
     }
 
