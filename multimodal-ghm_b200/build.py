@@ -16,11 +16,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "ghm_b200")
-BUILD = os.path.join(HERE, "build")
-LIB = os.path.join(OUT_DIR, "libghm_b200.so")
+BUILD = os.environ.get("GHM_BUILD_DIR") or os.path.join(HERE, "build")          # (development aids: an A/B library
+LIB = os.environ.get("GHM_LIB_OUT") or os.path.join(OUT_DIR, "libghm_b200.so")     #  built with other flags elsewhere)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+FLAGS += os.environ.get("GHM_EXTRA_FLAGS", "").split()
 
 
 _INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
@@ -56,6 +57,9 @@ def _compile(src, force, verbose):
     hh = _deps_hash(src)
     if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == hh:
         return obj, False, ""
+    only = os.environ.get("GHM_BUILD_ONLY")              # development aid: recompile only the sources whose name contains
+    if only and only not in os.path.basename(src) and os.path.exists(obj):   # this string, link the other (stale) objects
+        return obj, False, ""
     cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -73,7 +77,7 @@ def build(force=False, verbose=False):
 
     def cost(path):                                      # longest translation units first: they are the long pole of a
         name = os.path.basename(path)                    # parallel build (q = 16 instantiations take 2-3 minutes each)
-        return -(4 if "q16" in name else 3 if ("guides" in name or "q10" in name) else 2 if "_inst_" in name else 1)
+        return -(4 if "q16" in name else 3 if ("guides" in name or "q10" in name) else 2 if ("_inst_" in name or "_fast_" in name) else 1)
     srcs.sort(key=lambda p: (cost(p), p))
     with cf.ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
         res = list(ex.map(lambda s: _compile(s, force, verbose), srcs))

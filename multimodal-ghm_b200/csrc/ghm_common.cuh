@@ -46,8 +46,33 @@ struct GhmDev {
     const float* py;                       // [QP] prior, zero padded
     const uint32_t* root_cdfu_prior;       // [QP]
     const uint32_t* root_cdfu_unif;        // [QP]
+    const float* leaf_memo;                // [s][q^s][QS] f32: message of a depth-(L-1) node to its parent as a function of
+                                           //   (child number, its s leaf states), see ghm_leaf_memo_rows; null when not built
     int* status;                           // sticky device status word
 };
+
+// Leaf memo of the fused sampler + root-posterior kernel (ghm_tree_fast.cuh).  The upward message a depth-(L-1) node
+// sends to its parent, u = T_cj normalise(prod_c T_c^T[x_c, :]) (reference :191-208), depends on nothing but the
+// node's child number cj and the states (x_0 .. x_{s-1}) of its s leaves, so for translation-invariant tables it is
+// tabulated once per table upload (s * q^s rows of QS floats, built on the device by k_build_leaf_memo with the very
+// operations the kernel used to perform per node) and the kernel gathers one row instead of s leaf rows + a q x q
+// matvec.  Built when the whole table stays small against L2 (<= 1 MB at the padded q).
+#define GHM_MEMO_MAX_BYTES (1u << 20)
+constexpr bool ghm_memo_ok(int Q, int S) {
+#ifdef GHM_NO_LEAF_MEMO                                           // A/B builds only
+    return false;
+#endif
+    if (S < 2 || S > 4) return false;
+    size_t rows = (size_t)S;
+    for (int i = 0; i < S; ++i) rows *= (size_t)Q;
+    return rows * (size_t)((Q + 3) / 4 * 4) * 4 <= GHM_MEMO_MAX_BYTES;
+}
+static inline size_t ghm_leaf_memo_rows(const GhmDev& d) {      // 0: this model has no memo
+    if (!d.ti || d.L < 3 || d.QW || !ghm_memo_ok(d.QP, d.s)) return 0;
+    size_t rows = (size_t)d.s;
+    for (int i = 0; i < d.s; ++i) rows *= (size_t)d.q;
+    return rows;
+}
 
 // Source-offset tables of the fused guide kernels (ghm_guides.cu): for every 4- or 8-byte unit of a tree's row in
 // every guide tensor, the shared-memory offset (in floats) of the message element it copies.  A pure function of
@@ -107,6 +132,7 @@ private:
 };
 
 int ghm_guides_init(ghm_model* m);        // ghm_guides.cu: builds guide_tab (current device = m->device)
+int ghm_build_leaf_memo(const ghm_model* m, cudaStream_t st);   // ghm_tree.cu: fills d.leaf_memo from d.TTp on `st` (no-op without a memo)
 
 // ------------------------------------------------------------------------------------
 // error plumbing

@@ -46,7 +46,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // table derivation: host slab (pinned) with exactly the device slab's layout
 // ------------------------------------------------------------------------------------------------
 struct SlabLayout {
-    size_t Tlin, TlinT, TlogT, TTp, alias, cdfd, Wup, Wdn, py, rcp, rcu, status, bytes;
+    size_t Tlin, TlinT, TlogT, TTp, alias, cdfd, Wup, Wdn, py, rcp, rcu, status, memo, host_bytes, bytes;
 };
 
 static SlabLayout slab_layout(const GhmDev& d) {
@@ -61,6 +61,8 @@ static SlabLayout slab_layout(const GhmDev& d) {
     const size_t PW = (size_t)(d.QW > d.QP ? d.QW : d.QP);
     o.py = take(PW * 4); o.rcp = take((size_t)d.QP * 4); o.rcu = take((size_t)d.QP * 4);
     o.status = take(sizeof(int));
+    o.host_bytes = off;                                          // the pinned host image ends here: what follows is derived ON the device
+    o.memo = take(ghm_leaf_memo_rows(d) * (size_t)d.QS * 4);
     o.bytes = off;
     return o;
 }
@@ -91,7 +93,7 @@ static int derive_tables(const GhmDev& d, const double* T_host, const double* p_
     const SlabLayout o = slab_layout(d);
     const int q = d.q, QP = d.QP, QS = d.QS;
     const size_t nm = (size_t)d.n_mat, QQ = (size_t)QP * QP;
-    memset(hs, 0, o.bytes);
+    memset(hs, 0, o.host_bytes);
     float* Tlin = (float*)(hs + o.Tlin); float* TlinT = (float*)(hs + o.TlinT); float* TlogT = (float*)(hs + o.TlogT);
     float* Wup = (float*)(hs + o.Wup); float* Wdn = (float*)(hs + o.Wdn);
     float* TTp = (float*)(hs + o.TTp); uint32_t* alias = (uint32_t*)(hs + o.alias); double* cdfd = (double*)(hs + o.cdfd);
@@ -170,6 +172,7 @@ static void point_tables(ghm_model* m, int which) {
     d.py = (const float*)(base + o.py);
     d.root_cdfu_prior = (const uint32_t*)(base + o.rcp);
     d.root_cdfu_unif = (const uint32_t*)(base + o.rcu);
+    d.leaf_memo = ghm_leaf_memo_rows(d) ? (const float*)(base + o.memo) : nullptr;
     char* hb = (char*)m->h_slabs[which];
     m->h_TTp = (float*)(hb + o.TTp);
     m->h_Tlin = (float*)(hb + o.Tlin);
@@ -234,11 +237,11 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
         }                                                                                    \
     } while (0)
     MC_TRY(cudaSetDevice(device));
-    MC_TRY(cudaMallocHost(&m->h_slab, o.bytes));
+    MC_TRY(cudaMallocHost(&m->h_slab, o.host_bytes));
     int rc = derive_tables(d, T_host, p_y_host, (char*)m->h_slab);
     if (rc) { cudaSetDevice(prev); ghm_model_destroy(m); return rc; }
     MC_TRY(cudaMalloc(&m->slab, o.bytes));
-    MC_TRY(cudaMemcpy(m->slab, m->h_slab, o.bytes, cudaMemcpyHostToDevice));
+    MC_TRY(cudaMemcpy(m->slab, m->h_slab, o.host_bytes, cudaMemcpyHostToDevice));
     MC_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     MC_TRY(cudaEventCreateWithFlags(&m->upload_done, cudaEventDisableTiming));
     MC_TRY(cudaEventCreateWithFlags(&m->order_ev, cudaEventDisableTiming));
@@ -248,6 +251,12 @@ extern "C" int ghm_model_create(ghm_model_t** out, int L, int s, int q, int ti, 
     m->slabs[1] = nullptr; m->h_slabs[1] = nullptr; m->upload_evs[1] = nullptr;
     d.status = (int*)((char*)m->slab + o.status);              // the sticky status word stays in slab 0 for the model's lifetime
     point_tables(m, 0);
+    {                                                            // device-derived tables of slab 0
+        GhmDeviceGuard guard(device);
+        rc = ghm_build_leaf_memo(m, m->stream);
+        if (!rc && cudaStreamSynchronize(m->stream) != cudaSuccess) rc = ghm_fail(GHM_ECUDA, "leaf memo build failed");
+        if (rc) { ghm_model_destroy(m); return rc; }
+    }
     rc = ghm_guides_init(m);
     if (rc) { ghm_model_destroy(m); return rc; }
     *out = m;
@@ -271,7 +280,7 @@ extern "C" int ghm_model_update(ghm_model_t* m, const double* T_host, const doub
     const SlabLayout o = slab_layout(m->d);
     const int next = 1 - m->active;
     if (!m->slabs[next]) {                                       // first update: the second buffer pair
-        GHM_CUDA_TRY(cudaMallocHost(&m->h_slabs[next], o.bytes));
+        GHM_CUDA_TRY(cudaMallocHost(&m->h_slabs[next], o.host_bytes));
         GHM_CUDA_TRY(cudaMalloc(&m->slabs[next], o.bytes));
         GHM_CUDA_TRY(cudaEventCreateWithFlags(&m->upload_evs[next], cudaEventDisableTiming));
     }
@@ -279,9 +288,10 @@ extern "C" int ghm_model_update(ghm_model_t* m, const double* T_host, const doub
     int rc = derive_tables(m->d, T_host, p_y_host, (char*)m->h_slabs[next]);
     if (rc) return rc;
     GHM_CUDA_TRY(cudaMemcpyAsync(m->slabs[next], m->h_slabs[next], o.status, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    GHM_CUDA_TRY(cudaEventRecord(m->upload_evs[next], (cudaStream_t)stream));
     point_tables(m, next);
-    return GHM_OK;
+    rc = ghm_build_leaf_memo(m, (cudaStream_t)stream);           // device-derived tables of the new slab, behind its upload
+    GHM_CUDA_TRY(cudaEventRecord(m->upload_evs[next], (cudaStream_t)stream));
+    return rc;
 }
 
 extern "C" int ghm_model_set_gemm_mode(ghm_model_t* m, int mode) {

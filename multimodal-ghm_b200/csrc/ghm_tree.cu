@@ -52,6 +52,54 @@ __global__ void __launch_bounds__(PAR_NT) k_sample_parity(const GhmDev d, const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_build_leaf_memo: one thread per (child number cj, leaf states x_0 .. x_{s-1}) tabulates the message a
+// depth-(L-1) node sends to its parent (ghm_common.cuh, GhmDev::leaf_memo).  The row is produced with the
+// operations, in the order, of the per-node code it replaces in k_tree_fast / k_tree2 (product of the leaf rows
+// c = 0 .. s-1, max-rescale through the approximate reciprocal, packed FMA matvec over b = 0 .. Q-1), so the
+// memoised kernel returns bit-identical posteriors.  Reference: GHMTree.BP_CLS :191-208.
+// ------------------------------------------------------------------------------------------------
+template <int Q>
+__global__ void __launch_bounds__(128) k_build_leaf_memo(const GhmDev d, float* __restrict__ out, int rows) {
+    constexpr int H = Q / 2, QS = (Q + 3) / 4 * 4;
+    const int r = blockIdx.x * 128 + threadIdx.x;
+    if (r >= rows) return;
+    const int q = d.q, s = d.s, L = d.L;
+    int x[4], rem = r;
+    for (int c = s - 1; c >= 0; --c) { x[c] = rem % q; rem /= q; }   // row = ((cj*q + x_0)*q + x_1)*q + ...
+    const int cj = rem;
+    f2 h[H];
+    for (int c = 0; c < s; ++c) {
+        f2 row[H];
+        f2_load_row<Q>(d.TTp + ((size_t)(d.mat_off[L] + c) * Q + x[c]) * QS, row);
+#pragma unroll
+        for (int i = 0; i < H; ++i) h[i] = c == 0 ? row[i] : f2_mul(h[i], row[i]);
+    }
+    f2_normalize<Q>(h);
+    f2 u[H];
+    f2_matvec_up1<Q, QS>(d.TTp + (size_t)(d.mat_off[L - 1] + cj) * Q * QS, h, u);
+    float* o = out + (size_t)r * QS;
+#pragma unroll
+    for (int k = 0; k < QS; ++k) o[k] = k < Q ? f2_elem<Q>(u, k) : 0.f;
+}
+
+int ghm_build_leaf_memo(const ghm_model* m, cudaStream_t st) {
+    const GhmDev& d = m->d;
+    const size_t rows = ghm_leaf_memo_rows(d);
+    if (!rows || !d.leaf_memo) return GHM_OK;
+    float* out = const_cast<float*>(d.leaf_memo);
+    const unsigned grid = (unsigned)((rows + 127) / 128);
+    switch (d.QP) {
+        case 4: k_build_leaf_memo<4><<<grid, 128, 0, st>>>(d, out, (int)rows); break;
+        case 8: k_build_leaf_memo<8><<<grid, 128, 0, st>>>(d, out, (int)rows); break;
+        case 10: k_build_leaf_memo<10><<<grid, 128, 0, st>>>(d, out, (int)rows); break;
+        case 16: k_build_leaf_memo<16><<<grid, 128, 0, st>>>(d, out, (int)rows); break;
+        default: return ghm_fail(GHM_EUNSUP, "internal: leaf memo for padded q = %d", d.QP);
+    }
+    GHM_CHECK_LAUNCH();
+    return GHM_OK;
+}
+
 #ifdef GHM_TREE_PROBE   // development aid: compile one instantiation only (nvcc -DGHM_TREE_PROBE=2 -cubin)
 template __global__ void k_tree_fast<10, 3, MODE_PHILOX, true, 1536, false>(
     const __grid_constant__ GhmDev, const __grid_constant__ TreeArgs, const __grid_constant__ TabParam<1536>);

@@ -13,8 +13,45 @@
 //     j+1 (LDS chain, ALU pipe), and the BP climb of node j (packed FFMA2 with constant-bank operands) -- so
 //     the leaf-row product of the next node is in registers before the climb that needs it starts;
 //   * no odometer: child digits of the rarely taken deep steps come from `j / s^k` by the host's multiply-high
-//     magics (uniform datapath), the two hot steps use running counters.
+//     magics (uniform datapath), the two hot steps use running counters;
+//   * LEAF MEMO (where ghm_memo_ok(Q, S): the table stays <= 1 MB): the message of a depth-(L-1) node to its parent is a
+//     function of (child number, s leaf states) only, tabulated per table upload (GhmDev::leaf_memo, built on the device
+//     by k_build_leaf_memo with the same operations).  The node then costs ONE gathered row (L2 / L1 resident, fetched a
+//     full iteration ahead into the other half of a register ping-pong) instead of s shared-memory row gathers, the
+//     row product, a rescale and a q x q matvec: 27 of the 40 matvecs of an L = 4, s = 3 tree disappear.  The loop is
+//     unrolled by two so the prefetched row and the Philox block change roles without register copies.
 #pragma once
+
+// Flush of one warp's staged leaf bytes st[0 .. n) (n a multiple of 64) as n contiguous int64 at dst (16-byte aligned)
+// through two staging buffers carved from `buf` (buf_bytes >= 2048, 16-byte aligned, owned by this warp).
+__device__ __forceinline__ void stage_flush_bulk_i64(const uint8_t* st, int n, int64_t* dst, unsigned char* buf, int buf_bytes,
+                                                     int lane) {
+    const int per = min((buf_bytes / 2) / 512, 16) * 64;         // leaves per round: each lane expands per/32 (even) leaves
+    const uint32_t sbuf = (uint32_t)__cvta_generic_to_shared(buf);
+    const uint16_t* st16 = reinterpret_cast<const uint16_t*>(st);
+    __syncwarp();
+    int r = 0;
+    for (int g0 = 0; g0 < n; g0 += per, ++r) {
+        const int cnt = min(per, n - g0);                        // even
+        const int boff = (r & 1) * per * 8;
+        if (r >= 2) {                                            // the copy that last read this buffer has consumed it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+        }
+        for (int p = lane; 2 * p < cnt; p += 32) {               // leaves g0 + 2p, g0 + 2p + 1 -> 16 bytes at buffer offset 16 p
+            const uint32_t w = st16[(g0 >> 1) + p];
+            *reinterpret_cast<uint4*>(buf + boff + 16 * p) = make_uint4(w & 255u, 0u, w >> 8, 0u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
+                         :: "l"(dst + g0), "r"(sbuf + (uint32_t)boff), "r"(cnt * 8) : "memory");
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+}
 
 template <int Q, int S, int MODE, bool BP, int NW, bool BLK>
 __global__ void __launch_bounds__(T2_NT, 4)
@@ -23,6 +60,7 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
     constexpr int TPT = 2, NT = T2_NT, H = Q / 2, QS = (Q + 3) / 4 * 4, WTREES = 32 * TPT;
     constexpr bool SPARE = (S & 3) != 0;                         // node j is drawn from the spare word of its leaf block
     constexpr bool PHILOX = MODE == MODE_PHILOX;
+    constexpr bool MEMO = BP && PHILOX && ghm_memo_ok(Q, S);
     // Shared-memory stride of the gathered leaf rows T_c^T[x, :].  Each lane reads the row of ITS leaf state, so the
     // loads are true gathers: with 48-byte rows read as LDS.128 + LDS.128 + LDS.64 the ten rows of q = 10 fall on eight
     // 16-byte bank groups (rows 0/8 and 1/9 collide: 0.5 extra wavefronts per load, ncu r02k); with 40-byte rows read
@@ -39,7 +77,7 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
     size_t off = 0;
     const float* tt_leaf0 = nullptr;
     const uint32_t* AL = d.alias;
-    if (BP) {                                                    // leaf-level T^T rows are gathered per lane by leaf state
+    if (BP && !MEMO) {                                           // leaf-level T^T rows are gathered per lane by leaf state
         const int first = d.mat_off[L];
         const int words = S * Q * LS;
         float* s1 = reinterpret_cast<float*>(smem + off); off += ((size_t)words * 4 + 15) / 16 * 16;
@@ -54,7 +92,10 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
         AL = s2;
     }
     const int n_deep = L - 2;                                    // ancestors kept in shared memory: depths 0 .. L-3
-    f2* ACC = reinterpret_cast<f2*>(smem + off);                 // [n_deep][H][TPT][NT]
+    // [warp][n_deep][H][TPT][32]: a warp's accumulators are one contiguous span, reused as the staging buffers of the
+    // bulk-store flush once the last climb is done
+    const int acc_warp = n_deep * H * TPT * 32;                  // f2 elements per warp
+    f2* ACC = reinterpret_cast<f2*>(smem + off) + (size_t)warp * acc_warp + lane;
     if (BP) off += (size_t)n_deep * H * TPT * NT * sizeof(f2);
     const int n_rng = n_deep + (SPARE ? 0 : 1);                  // levels 1 .. L-2 (+ L-1 when it has no spare word)
     uint32_t* RNG = reinterpret_cast<uint32_t*>(smem + off);     // [n_rng][3][TPT][NT]  words 1..3 of the cached Philox blocks
@@ -161,6 +202,9 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
                 xc[t] = ghm_draw_alias(arow + xpar[t] * q, r, q);
             }
         }
+        int mrow[TPT];                                           // MEMO: ((cjn * q + x_0) * q + x_1) * q + ...
+#pragma unroll
+        for (int t = 0; t < TPT; ++t) mrow[t] = cjn;
 #pragma unroll
         for (int c = 0; c < S; ++c) {
 #pragma unroll
@@ -172,7 +216,9 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
                 } else {
                     x = stage[srow[t] + jn * S + c];
                 }
-                if (BP) {
+                if constexpr (MEMO) {
+                    mrow[t] = mrow[t] * q + x;
+                } else if (BP) {
                     f2 row[H];
                     if constexpr (LS == Q) {
                         const f2* rp = reinterpret_cast<const f2*>(tt_leaf0 + (c * Q + x) * LS);
@@ -185,6 +231,10 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
                     for (int i = 0; i < H; ++i) hout[t][i] = c == 0 ? row[i] : f2_mul(hout[t][i], row[i]);
                 }
             }
+        }
+        if constexpr (MEMO) {                                    // one row of the memo per tree: first used one iteration later
+#pragma unroll
+            for (int t = 0; t < TPT; ++t) f2_ldg_row<Q>(d.leaf_memo + (size_t)(unsigned)mrow[t] * QS, hout[t]);
         }
     };
 
@@ -203,14 +253,14 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
 #pragma unroll
             for (int t = 0; t < TPT; ++t)
 #pragma unroll
-                for (int i = 0; i < H; ++i) u[t][i] = f2_mul(u[t][i], A ? A[(i * TPT + t) * NT] : accT[t][i]);
+                for (int i = 0; i < H; ++i) u[t][i] = f2_mul(u[t][i], A ? A[(i * TPT + t) * 32] : accT[t][i]);
         }
         if (!last) {
 #pragma unroll
             for (int t = 0; t < TPT; ++t)
 #pragma unroll
                 for (int i = 0; i < H; ++i) {
-                    if (A) A[(i * TPT + t) * NT] = u[t][i]; else accT[t][i] = u[t][i];
+                    if (A) A[(i * TPT + t) * 32] = u[t][i]; else accT[t][i] = u[t][i];
                 }
             return false;
         }
@@ -225,23 +275,37 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
 
     // the BP climb of node j, whose leaf-row product is h
     auto climb = [&](int j, int cj, int c1, const f2 (&h)[TPT][H]) {
+        bool up;
+        if constexpr (MEMO) {                                    // h IS the message to the parent: fold it into the parked product
+            up = cj == S - 1;
 #pragma unroll
-        for (int t = 0; t < TPT; ++t) {
+            for (int t = 0; t < TPT; ++t) {
 #pragma unroll
-            for (int i = 0; i < H; ++i) msg[t][i] = h[t][i];
-            f2_normalize<Q>(msg[t]);
+                for (int i = 0; i < H; ++i) {
+                    const f2 u = cj != 0 ? f2_mul(h[t][i], accT[t][i]) : h[t][i];
+                    if (up) msg[t][i] = u; else accT[t][i] = u;
+                }
+                if (up) f2_normalize<Q>(msg[t]);
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < TPT; ++t) {
+#pragma unroll
+                for (int i = 0; i < H; ++i) msg[t][i] = h[t][i];
+                f2_normalize<Q>(msg[t]);
+            }
+            // the two hottest steps (every node / every s-th node) read their table through running offsets that feed
+            // nothing but the constant-bank address, so they stay in UNIFORM registers (LDCU.64 + FFMA2 with a UR operand)
+            up = climb_step(tab.v + (base0 + cj) * (Q * QS), cj != 0, cj == S - 1, nullptr);
         }
-        // the two hottest steps (every node / every s-th node) read their table through running offsets that feed
-        // nothing but the constant-bank address, so they stay in UNIFORM registers (LDCU.64 + FFMA2 with a UR operand)
-        bool up = climb_step(tab.v + (base0 + cj) * (Q * QS), cj != 0, cj == S - 1, nullptr);
-        if (up) up = climb_step(tab.v + (base1 + c1) * (Q * QS), c1 != 0, c1 == S - 1, ACC + (size_t)(L - 3) * H * TPT * NT + tid);
+        if (up) up = climb_step(tab.v + (base1 + c1) * (Q * QS), c1 != 0, c1 == S - 1, ACC + (size_t)(L - 3) * H * TPT * 32);
         if (up && L >= 4) {
-            f2* A = ACC + (size_t)(L - 4) * H * TPT * NT + tid;
+            f2* A = ACC + (size_t)(L - 4) * H * TPT * 32;
             for (int l = L - 3; l > 0; --l) {
                 const int idx = ghm_div_pow(j, L - 1 - l, d);    // index of the path node at depth l
                 const int c = idx - (idx / S) * S;
                 if (!climb_step(tab.v + ((l - 1) * S + c) * (Q * QS), c != 0, c == S - 1, A)) break;
-                A -= H * TPT * NT;
+                A -= H * TPT * 32;
             }
         }
     };
@@ -253,40 +317,73 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
         redraw_ancestors(0);
 #pragma unroll
         for (int t = 0; t < TPT; ++t) {
-            rbA[t] = ghm_rng_block(a.seed, tree[t], (uint32_t)L, 0u, GHM_STREAM_TREE);
-            rbB[t] = ghm_rng_block(a.seed, tree[t], (uint32_t)L, 1u, GHM_STREAM_TREE);
+            rbB[t] = ghm_rng_block(a.seed, tree[t], (uint32_t)L, 0u, GHM_STREAM_TREE);
+            rbA[t] = ghm_rng_block(a.seed, tree[t], (uint32_t)L, 1u, GHM_STREAM_TREE);   // block of node 1
         }
     }
-    sample_node(0, 0, rbA, hcur);
-#pragma unroll
-    for (int t = 0; t < TPT; ++t) rbA[t] = rbB[t];               // block of node 1
+    sample_node(0, 0, rbB, hcur);
 
     int cj = 0, c1 = 0;                                          // j mod s, (j / s) mod s
-    for (int j = 0; j < n1 - 1; ++j) {
+    // One straight-line block: Philox of node j+2 (-> rbN), draws + leaf rows of node j+1 (rbU -> hL), BP climb of node j (hU).
+    // (measured: guarding the sampling half with `jn < n1` instead of peeling the last climb costs 4 %)
+    auto body = [&](int j, uint4 (&rbU)[TPT], uint4 (&rbN)[TPT], f2 (&hU)[TPT][H], f2 (&hL)[TPT][H]) {
         const int jn = j + 1;
         const int cjn = cj + 1 == S ? 0 : cj + 1;
         if (PHILOX && cjn == 0) redraw_ancestors(jn);
-        // ---- one straight-line block: Philox of node j+2, draws + leaf rows of node j+1, BP climb step of node j ----
-        // (measured: guarding the sampling half with `jn < n1` instead of peeling the last climb costs 4 %)
         if (PHILOX) {
 #pragma unroll
             for (int t = 0; t < TPT; ++t)                        // (one block past the end is computed and dropped)
-                rbB[t] = ghm_rng_block(a.seed, tree[t], (uint32_t)L, (uint32_t)(jn + 1), GHM_STREAM_TREE);
+                rbN[t] = ghm_rng_block(a.seed, tree[t], (uint32_t)L, (uint32_t)(jn + 1), GHM_STREAM_TREE);
         }
-        sample_node(jn, cjn, rbA, hnext);
-        if (BP) climb(j, cj, c1, hcur);
-#pragma unroll
-        for (int t = 0; t < TPT; ++t) {
-            rbA[t] = rbB[t];
-#pragma unroll
-            for (int i = 0; i < H; ++i) hcur[t][i] = hnext[t][i];
+        if constexpr (MEMO) {
+            // consume the prefetched row BEFORE the next gathers are issued: a wait placed behind them shares their
+            // scoreboard and sits out a full L2 round trip (ncu r02x: 29 % of the stall samples on the first use)
+            climb(j, cj, c1, hU);
+            sample_node(jn, cjn, rbU, hL);
+        } else {
+            sample_node(jn, cjn, rbU, hL);
+            if (BP) climb(j, cj, c1, hU);
         }
         cj = cjn;
         if (cjn == 0) c1 = c1 + 1 == S ? 0 : c1 + 1;
+    };
+    if constexpr (MEMO) {                                        // unrolled by two: the buffers swap roles, no register copies
+        int j = 0;
+        for (; j + 2 <= n1 - 1; j += 2) {
+            body(j, rbA, rbB, hcur, hnext);
+            body(j + 1, rbB, rbA, hnext, hcur);
+        }
+        if constexpr (S % 2 == 0) {                              // n1 = s^(L-1) even: one node pair is left (odd s: none)
+            body(j, rbA, rbB, hcur, hnext);
+            climb(n1 - 1, cj, c1, hnext);
+        } else {
+            climb(n1 - 1, cj, c1, hcur);
+        }
+    } else {
+        for (int j = 0; j < n1 - 1; ++j) {
+            body(j, rbA, rbB, hcur, hnext);
+#pragma unroll
+            for (int t = 0; t < TPT; ++t) {
+                rbA[t] = rbB[t];
+#pragma unroll
+                for (int i = 0; i < H; ++i) hcur[t][i] = hnext[t][i];
+            }
+        }
+        if (BP) climb(n1 - 1, cj, c1, hcur);
     }
-    if (BP) climb(n1 - 1, cj, c1, hcur);
 
-    if (PHILOX && use_stage) stage_flush_flat(stage, WTREES, a.leaves, a.leaf_dtype, warp_tree0, a.B, nL, lane);
+    if (PHILOX && use_stage) {
+        // int64 leaves of a full tile leave through the bulk-copy engine: the warp expands its staged bytes into two
+        // alternating buffers (its accumulator span, dead by now) with conflict-free STS.128 and one lane hands each
+        // filled buffer to cp.async.bulk.  The STG.128 loop it replaces ran one store at a time -- the next store's data
+        // registers were the previous store's, and each wait was a round trip of the busy LSU queue (ncu r02y: 28 % of
+        // the kernel's stall samples) -- and every CTA of a wave reached it at the same moment.
+        if (BP && a.leaf_dtype == GHM_LEAF_I64 && warp_tree0 + WTREES <= a.B && acc_warp * (int)sizeof(f2) >= 2048)
+            stage_flush_bulk_i64(stage, WTREES * nL, reinterpret_cast<int64_t*>(a.leaves) + warp_tree0 * nL,
+                                 reinterpret_cast<unsigned char*>(ACC - lane), acc_warp * (int)sizeof(f2), lane);
+        else
+            stage_flush_flat(stage, WTREES, a.leaves, a.leaf_dtype, warp_tree0, a.B, nL, lane);
+    }
 
     // ---- root outputs (reference :213-217; root_node.hd_message is the shifted log-likelihood) --
     if (BP) {
@@ -320,7 +417,9 @@ static int launch_tree_fast(const ghm_model* m, const TreeArgs& a0, cudaStream_t
     constexpr int QS = (Q + 3) / 4 * 4, WTREES = 64;
     const int n_deep = d.L - 2;
     size_t dyn = 0;
-    if (BP) dyn += ((size_t)S * Q * ((Q % 4 == 2 && MODE == MODE_GIVEN) ? Q : QS) * 4 + 15) / 16 * 16;
+    constexpr bool MEMO = BP && MODE == MODE_PHILOX && ghm_memo_ok(Q, S);
+    if (MEMO && !d.leaf_memo) return ghm_fail(GHM_EUNSUP, "internal: leaf memo missing (L=%d s=%d q=%d)", d.L, d.s, d.q);
+    if (BP && !MEMO) dyn += ((size_t)S * Q * ((Q % 4 == 2 && MODE == MODE_GIVEN) ? Q : QS) * 4 + 15) / 16 * 16;
     if (MODE == MODE_PHILOX) dyn += ((size_t)d.n_mat * d.q * d.q * 4 + 15) / 16 * 16;
     if (BP) dyn += (size_t)n_deep * (Q / 2) * 2 * T2_NT * sizeof(float2);
     if (MODE == MODE_PHILOX) {
@@ -331,7 +430,7 @@ static int launch_tree_fast(const ghm_model* m, const TreeArgs& a0, cudaStream_t
     a.base0 = (d.L - 2) * d.s; a.base1 = (d.L - 3) * d.s;
     if (a.leaves) {
         a.stage_stride = d.n_leaves;
-        a.stage_bytes = (int)(((size_t)WTREES * d.n_leaves + 15) / 16 * 16);
+        a.stage_bytes = (int)(((size_t)WTREES * a.stage_stride + 15) / 16 * 16);
     }
     dyn += (size_t)a.stage_bytes * T2_WARPS;
     if (dyn > 200 * 1024)

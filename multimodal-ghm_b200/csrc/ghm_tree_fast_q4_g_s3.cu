@@ -1,0 +1,4 @@
+// k_tree_fast instantiations for padded q = 4, mode "g", s = 3 (see ghm_tree_kernel.cuh / ghm_tree_fast.cuh)
+#include "ghm_tree_kernel.cuh"
+
+GHM_TREE_FAST_DEFINE(4, g, MODE_GIVEN, true, 3)

@@ -1,4 +1,4 @@
 // k_tree2 instantiations for padded q = 4, mode "g" (see ghm_tree_kernel.cuh)
 #include "ghm_tree_kernel.cuh"
 
-GHM_TREE_DEFINE(4, g, MODE_GIVEN, true)
+GHM_TREE_DEFINE_SPLIT(4, g, MODE_GIVEN, true)

@@ -1,4 +1,4 @@
 // k_tree2 instantiations for padded q = 8, mode "sb" (see ghm_tree_kernel.cuh)
 #include "ghm_tree_kernel.cuh"
 
-GHM_TREE_DEFINE(8, sb, MODE_PHILOX, true)
+GHM_TREE_DEFINE_SPLIT(8, sb, MODE_PHILOX, true)

@@ -589,8 +589,12 @@ static int launch_fast(const ghm_model* m, const TreeArgs& a, cudaStream_t st) {
     return launch_tree_fast<Q, S, MODE, BP, 6144>(m, a, st);
 }
 
+typedef int (*ghm_fast_fn)(const ghm_model*, const TreeArgs&, cudaStream_t);
+
+// fast[k]: the software-pipelined variant for s = 2 + k.  The fused-BP modes compile each of them in a translation
+// unit of its own (ghm_tree_fast_q*_s*.cu: they are the long pole of the build), sampling-only instantiates them here.
 template <int Q, int MODE, bool BP>
-static int dispatch_variant(const ghm_model* m, const TreeArgs& a, cudaStream_t st) {
+static int dispatch_variant(const ghm_model* m, const TreeArgs& a, cudaStream_t st, const ghm_fast_fn (&fast)[3]) {
     const GhmDev& d = m->d;
     constexpr int QS = (Q + 3) / 4 * 4;
     const size_t ctab_words = (size_t)d.n_mat * Q * QS;
@@ -599,13 +603,8 @@ static int dispatch_variant(const ghm_model* m, const TreeArgs& a, cudaStream_t 
     if (MODE == MODE_PHILOX) smem_tab += ((size_t)d.n_mat * d.q * d.q * 4 + 15) / 16 * 16;
     const size_t flat_bytes = a.leaves ? ((size_t)64 * d.n_leaves + 15) / 16 * 16 * T2_WARPS : 0;
     const bool flat_ok = !a.leaves || (flat_bytes <= 48 * 1024 && ((uintptr_t)a.leaves % 16) == 0);
-    if (d.ti && d.L >= 3 && ctab_words <= 6144 && smem_tab <= 40 * 1024 && flat_ok && d.s >= 2 && d.s <= 4) {
-        switch (d.s) {                                             // software-pipelined variant (ghm_tree_fast.cuh)
-            case 2: return launch_fast<Q, 2, MODE, BP>(m, a, st);
-            case 3: return launch_fast<Q, 3, MODE, BP>(m, a, st);
-            default: return launch_fast<Q, 4, MODE, BP>(m, a, st);
-        }
-    }
+    if (d.ti && d.L >= 3 && ctab_words <= 6144 && smem_tab <= 40 * 1024 && flat_ok && d.s >= 2 && d.s <= 4)
+        return fast[d.s - 2](m, a, st);                            // software-pipelined variant (ghm_tree_fast.cuh)
     size_t gen_tab = 0;
     if (BP) gen_tab += (size_t)d.n_mat * Q * QS * 4;
     if (MODE == MODE_PHILOX) gen_tab += ((size_t)d.n_mat * d.q * d.q * 4 + 15) / 16 * 16;
@@ -614,5 +613,24 @@ static int dispatch_variant(const ghm_model* m, const TreeArgs& a, cudaStream_t 
 
 // one translation unit per (padded q, mode): ghm_tree_inst_*.cu define these
 #define GHM_TREE_DECLARE(Q, TAG) int ghm_tree_run_q##Q##_##TAG(const ghm_model* m, const TreeArgs& a, cudaStream_t st);
-#define GHM_TREE_DEFINE(Q, TAG, MODE, BP) \
-    int ghm_tree_run_q##Q##_##TAG(const ghm_model* m, const TreeArgs& a, cudaStream_t st) { return dispatch_variant<Q, MODE, BP>(m, a, st); }
+#define GHM_TREE_DEFINE(Q, TAG, MODE, BP)                                                                          \
+    int ghm_tree_run_q##Q##_##TAG(const ghm_model* m, const TreeArgs& a, cudaStream_t st) {                         \
+        static const ghm_fast_fn fast[3] = {&launch_fast<Q, 2, MODE, BP>, &launch_fast<Q, 3, MODE, BP>,             \
+                                            &launch_fast<Q, 4, MODE, BP>};                                          \
+        return dispatch_variant<Q, MODE, BP>(m, a, st, fast);                                                      \
+    }
+// ... with the fast variants in ghm_tree_fast_q<Q>_<TAG>_s<S>.cu (GHM_TREE_FAST_DEFINE)
+#define GHM_TREE_FAST_NAME(Q, TAG, S) ghm_tree_fast_q##Q##_##TAG##_s##S
+#define GHM_TREE_FAST_DEFINE(Q, TAG, MODE, BP, S)                                                                  \
+    int GHM_TREE_FAST_NAME(Q, TAG, S)(const ghm_model* m, const TreeArgs& a, cudaStream_t st) {                     \
+        return launch_fast<Q, S, MODE, BP>(m, a, st);                                                              \
+    }
+#define GHM_TREE_DEFINE_SPLIT(Q, TAG, MODE, BP)                                                                    \
+    int GHM_TREE_FAST_NAME(Q, TAG, 2)(const ghm_model*, const TreeArgs&, cudaStream_t);                             \
+    int GHM_TREE_FAST_NAME(Q, TAG, 3)(const ghm_model*, const TreeArgs&, cudaStream_t);                             \
+    int GHM_TREE_FAST_NAME(Q, TAG, 4)(const ghm_model*, const TreeArgs&, cudaStream_t);                             \
+    int ghm_tree_run_q##Q##_##TAG(const ghm_model* m, const TreeArgs& a, cudaStream_t st) {                         \
+        static const ghm_fast_fn fast[3] = {&GHM_TREE_FAST_NAME(Q, TAG, 2), &GHM_TREE_FAST_NAME(Q, TAG, 3),         \
+                                            &GHM_TREE_FAST_NAME(Q, TAG, 4)};                                        \
+        return dispatch_variant<Q, MODE, BP>(m, a, st, fast);                                                      \
+    }

@@ -49,6 +49,20 @@ __device__ __forceinline__ void f2_load_row(const float* __restrict__ row, f2 (&
     if constexpr (Q % 4 == 2) out[Q / 2 - 1] = *reinterpret_cast<const float2*>(row + Q - 2);
 }
 
+// the same row through the read-only data path (ld.global.nc: L1-cacheable gathers of a table that lives in L2)
+template <int Q>
+__device__ __forceinline__ void f2_ldg_row(const float* __restrict__ row, f2 (&out)[Q / 2]) {
+    static_assert(Q % 2 == 0, "even Q");
+    const float4* p4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+    for (int i = 0; i < Q / 4; ++i) {
+        const float4 v = __ldg(p4 + i);
+        out[2 * i] = make_float2(v.x, v.y);
+        out[2 * i + 1] = make_float2(v.z, v.w);
+    }
+    if constexpr (Q % 4 == 2) out[Q / 2 - 1] = __ldg(reinterpret_cast<const float2*>(row + Q - 2));
+}
+
 template <int Q>
 __device__ __forceinline__ float f2_elem(const f2 (&x)[Q / 2], int b) { return (b & 1) ? x[b >> 1].y : x[b >> 1].x; }
 

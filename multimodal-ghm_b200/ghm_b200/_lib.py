@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libghm_b200.so")
+LIB_PATH = os.environ.get("GHM_LIB_PATH") or os.path.join(_HERE, "libghm_b200.so")   # (override: A/B builds, development only)
 
 _lib = None
 

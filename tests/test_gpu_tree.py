@@ -52,7 +52,9 @@ def test_bp_cls_vs_reference_fixture(ops, name):
 
 @pytest.mark.parametrize("L,s,q,ti,B", [(4, 3, 10, True, 4099), (3, 4, 10, True, 1000), (6, 2, 7, False, 513),
                                          (2, 8, 16, True, 300), (9, 2, 3, True, 200), (4, 3, 10, False, 777),
-                                         (1, 5, 12, True, 65), (3, 3, 2, True, 129)])
+                                         (1, 5, 12, True, 65), (3, 3, 2, True, 129),
+                                         # leaf-memo shapes of every padded q (ghm_common.cuh: ghm_memo_ok), q < padded q included
+                                         (3, 3, 16, True, 333), (4, 2, 8, True, 515), (3, 4, 7, True, 260), (5, 2, 13, True, 131)])
 def test_sampling_and_bp_vs_oracle(ops, L, s, q, ti, B):
     """Seeded larger batches (ragged tails, n_L > 256 chunking, per-edge tables) against the oracle."""
     from oracle import ghm_oracle as O
@@ -76,7 +78,8 @@ def test_sampling_and_bp_vs_oracle(ops, L, s, q, ti, B):
 
 @pytest.mark.parametrize("L,s,q,ti,B", [(4, 3, 10, True, 1031), (3, 2, 5, False, 200), (2, 4, 16, True, 97),
                                         (1, 3, 4, True, 70), (2, 2, 8, True, 300), (3, 5, 6, True, 130),
-                                        (3, 8, 10, True, 150), (5, 2, 4, False, 100), (3, 4, 10, True, 257)])
+                                        (3, 8, 10, True, 150), (5, 2, 4, False, 100), (3, 4, 10, True, 257),
+                                        (3, 3, 16, True, 190), (4, 2, 8, True, 321), (3, 4, 6, True, 129), (4, 3, 9, True, 200)])
 def test_philox_sampling_bit_exact_vs_philox_oracle(ops, L, s, q, ti, B):
     """Philox mode: leaves, roots and fused BP must match the NumPy Philox restatement exactly."""
     from oracle import ghm_oracle as O, philox
