@@ -101,8 +101,12 @@ int ghm_build_leaf_memo(const ghm_model* m, cudaStream_t st) {
 }
 
 #ifdef GHM_TREE_PROBE   // development aid: compile one instantiation only (nvcc -DGHM_TREE_PROBE=2 -cubin)
-template __global__ void k_tree_fast<10, 3, MODE_PHILOX, true, 1536, false>(
-    const __grid_constant__ GhmDev, const __grid_constant__ TreeArgs, const __grid_constant__ TabParam<1536>);
+#ifndef GHM_PROBE_Q
+#define GHM_PROBE_Q 10
+#define GHM_PROBE_S 3
+#endif
+template __global__ void k_tree_fast<GHM_PROBE_Q, GHM_PROBE_S, MODE_PHILOX, true, 6144, false>(
+    const __grid_constant__ GhmDev, const __grid_constant__ TreeArgs, const __grid_constant__ TabParam<6144>);
 #endif
 
 #ifndef GHM_TREE_PROBE

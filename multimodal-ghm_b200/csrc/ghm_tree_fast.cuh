@@ -22,8 +22,8 @@
 //     unrolled by two so the prefetched row and the Philox block change roles without register copies.
 #pragma once
 
-// Flush of one warp's staged leaf bytes st[0 .. n) (n a multiple of 64) as n contiguous int64 at dst (16-byte aligned)
-// through two staging buffers carved from `buf` (buf_bytes >= 2048, 16-byte aligned, owned by this warp).
+// Flush of one warp's staged leaf bytes st[0 .. n) (n even) as n contiguous int64 at dst (16-byte aligned)
+// through two staging buffers carved from `buf` (buf_bytes >= 1024, 16-byte aligned, owned by this warp).
 __device__ __forceinline__ void stage_flush_bulk_i64(const uint8_t* st, int n, int64_t* dst, unsigned char* buf, int buf_bytes,
                                                      int lane) {
     const int per = min((buf_bytes / 2) / 512, 16) * 64;         // leaves per round: each lane expands per/32 (even) leaves
@@ -53,14 +53,26 @@ __device__ __forceinline__ void stage_flush_bulk_i64(const uint8_t* st, int n, i
     __syncwarp();
 }
 
+// Shape of a variant.  With the leaf memo the kernel is short of warps, not of issue slots (ncu r02z: 4 warps per
+// scheduler, issue 0.48, every pipe under 0.36), and what two trees per thread used to share -- the constant-bank table
+// loads of the leaf-level matvec -- is gone: ONE tree per thread in 70-80 registers and half the shared memory puts 7
+// (q <= 10) or 6 CTAs on an SM instead of 4 (measured, L4 s3 q10: 0.1524 -> 0.1390 ms).  Without the memo the two-tree
+// form stays (one tree per thread measured equal there).
+template <int Q, int S, int MODE, bool BP>
+struct FastCfg {
+    static constexpr bool MEMO = BP && MODE == MODE_PHILOX && ghm_memo_ok(Q, S);
+    static constexpr int TPT = MEMO ? 1 : 2;
+    static constexpr int CTAS = MEMO ? (Q <= 10 ? 7 : 6) : 4;
+};
+
 template <int Q, int S, int MODE, bool BP, int NW, bool BLK>
-__global__ void __launch_bounds__(T2_NT, 4)
+__global__ void __launch_bounds__(T2_NT, (FastCfg<Q, S, MODE, BP>::CTAS))
 k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a, const __grid_constant__ TabParam<NW> tab) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int TPT = 2, NT = T2_NT, H = Q / 2, QS = (Q + 3) / 4 * 4, WTREES = 32 * TPT;
+    constexpr int TPT = FastCfg<Q, S, MODE, BP>::TPT, NT = T2_NT, H = Q / 2, QS = (Q + 3) / 4 * 4, WTREES = 32 * TPT;
     constexpr bool SPARE = (S & 3) != 0;                         // node j is drawn from the spare word of its leaf block
     constexpr bool PHILOX = MODE == MODE_PHILOX;
-    constexpr bool MEMO = BP && PHILOX && ghm_memo_ok(Q, S);
+    constexpr bool MEMO = FastCfg<Q, S, MODE, BP>::MEMO;
     // Shared-memory stride of the gathered leaf rows T_c^T[x, :].  Each lane reads the row of ITS leaf state, so the
     // loads are true gathers: with 48-byte rows read as LDS.128 + LDS.128 + LDS.64 the ten rows of q = 10 fall on eight
     // 16-byte bank groups (rows 0/8 and 1/9 collide: 0.5 extra wavefronts per load, ncu r02k); with 40-byte rows read
@@ -248,7 +260,8 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
     // siblings to come) or rescale and keep climbing.  A == nullptr: register accumulator.
     auto climb_step = [&](const float* __restrict__ Tm, bool has_prev, bool last, f2* A) -> bool {
         f2 u[TPT][H];
-        f2_matvec_up2<Q, QS>(Tm, msg[0], msg[1], u[0], u[1]);
+        if constexpr (TPT == 2) f2_matvec_up2<Q, QS>(Tm, msg[0], msg[1], u[0], u[1]);
+        else f2_matvec_up1<Q, QS>(Tm, msg[0], u[0]);
         if (has_prev) {
 #pragma unroll
             for (int t = 0; t < TPT; ++t)
@@ -378,7 +391,7 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
         // filled buffer to cp.async.bulk.  The STG.128 loop it replaces ran one store at a time -- the next store's data
         // registers were the previous store's, and each wait was a round trip of the busy LSU queue (ncu r02y: 28 % of
         // the kernel's stall samples) -- and every CTA of a wave reached it at the same moment.
-        if (BP && a.leaf_dtype == GHM_LEAF_I64 && warp_tree0 + WTREES <= a.B && acc_warp * (int)sizeof(f2) >= 2048)
+        if (BP && a.leaf_dtype == GHM_LEAF_I64 && warp_tree0 + WTREES <= a.B && acc_warp * (int)sizeof(f2) >= 1024)
             stage_flush_bulk_i64(stage, WTREES * nL, reinterpret_cast<int64_t*>(a.leaves) + warp_tree0 * nL,
                                  reinterpret_cast<unsigned char*>(ACC - lane), acc_warp * (int)sizeof(f2), lane);
         else
@@ -414,17 +427,17 @@ template <int Q, int S, int MODE, bool BP, int NW>
 static int launch_tree_fast(const ghm_model* m, const TreeArgs& a0, cudaStream_t st) {
     const GhmDev& d = m->d;
     TreeArgs a = a0;
-    constexpr int QS = (Q + 3) / 4 * 4, WTREES = 64;
+    constexpr int QS = (Q + 3) / 4 * 4, TPT = FastCfg<Q, S, MODE, BP>::TPT, WTREES = 32 * TPT;
     const int n_deep = d.L - 2;
     size_t dyn = 0;
-    constexpr bool MEMO = BP && MODE == MODE_PHILOX && ghm_memo_ok(Q, S);
+    constexpr bool MEMO = FastCfg<Q, S, MODE, BP>::MEMO;
     if (MEMO && !d.leaf_memo) return ghm_fail(GHM_EUNSUP, "internal: leaf memo missing (L=%d s=%d q=%d)", d.L, d.s, d.q);
     if (BP && !MEMO) dyn += ((size_t)S * Q * ((Q % 4 == 2 && MODE == MODE_GIVEN) ? Q : QS) * 4 + 15) / 16 * 16;
     if (MODE == MODE_PHILOX) dyn += ((size_t)d.n_mat * d.q * d.q * 4 + 15) / 16 * 16;
-    if (BP) dyn += (size_t)n_deep * (Q / 2) * 2 * T2_NT * sizeof(float2);
+    if (BP) dyn += (size_t)n_deep * (Q / 2) * TPT * T2_NT * sizeof(float2);
     if (MODE == MODE_PHILOX) {
         const int n_rng = n_deep + ((S & 3) != 0 ? 0 : 1);
-        dyn += (size_t)n_rng * 3 * 2 * T2_NT * 4 + ((size_t)n_deep * 2 * T2_NT + 15) / 16 * 16;
+        dyn += (size_t)n_rng * 3 * TPT * T2_NT * 4 + ((size_t)n_deep * TPT * T2_NT + 15) / 16 * 16;
     }
     a.chunk_j = d.spow[d.L - 1]; a.stage_stride = 0; a.stage_bytes = 0;
     a.base0 = (d.L - 2) * d.s; a.base1 = (d.L - 3) * d.s;
