@@ -22,34 +22,54 @@
 //     unrolled by two so the prefetched row and the Philox block change roles without register copies.
 #pragma once
 
-// Flush of one warp's staged leaf bytes st[0 .. n) (n even) as n contiguous int64 at dst (16-byte aligned)
-// through two staging buffers carved from `buf` (buf_bytes >= 1024, 16-byte aligned, owned by this warp).
-__device__ __forceinline__ void stage_flush_bulk_i64(const uint8_t* st, int n, int64_t* dst, unsigned char* buf, int buf_bytes,
-                                                     int lane) {
-    const int per = min((buf_bytes / 2) / 512, 16) * 64;         // leaves per round: each lane expands per/32 (even) leaves
+// Flush of one warp's staged leaf bytes st[0 .. n) (n a multiple of 32) as n contiguous int64 at dst (16-byte aligned)
+// through a ring of nb (1 .. 4) staging buffers of 1 KB carved from `buf` (16-byte aligned, owned by this warp).  A round
+// moves 128 leaves: every lane expands two byte pairs with one conflict-free STS.128 each, lane 0 hands the buffer to
+// the bulk-copy engine and then waits until the ring has a free buffer again, so nb - 1 copies stay in flight.
+__device__ __forceinline__ void bulk_wait_read(int pending) {    // cp.async.bulk.wait_group.read takes an immediate
+    if (pending <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    else if (pending == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    else if (pending == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+}
+__device__ __forceinline__ void stage_flush_bulk_i64(const uint8_t* st, int n, int64_t* dst, unsigned char* buf, int nb, int lane) {
     const uint32_t sbuf = (uint32_t)__cvta_generic_to_shared(buf);
-    const uint16_t* st16 = reinterpret_cast<const uint16_t*>(st);
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(st) + lane;
+    unsigned char* my = buf + 16 * lane;
+    const int rounds = n >> 7, tail = n & 127;                   // tail: 0, 32, 64 or 96 leaves
+    int b = 0;
     __syncwarp();
-    int r = 0;
-    for (int g0 = 0; g0 < n; g0 += per, ++r) {
-        const int cnt = min(per, n - g0);                        // even
-        const int boff = (r & 1) * per * 8;
-        if (r >= 2) {                                            // the copy that last read this buffer has consumed it
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncwarp();
-        }
-        for (int p = lane; 2 * p < cnt; p += 32) {               // leaves g0 + 2p, g0 + 2p + 1 -> 16 bytes at buffer offset 16 p
-            const uint32_t w = st16[(g0 >> 1) + p];
-            *reinterpret_cast<uint4*>(buf + boff + 16 * p) = make_uint4(w & 255u, 0u, w >> 8, 0u);
-        }
+    for (int r = 0; r < rounds; ++r) {
+        const uint32_t w0 = src[0], w1 = src[32];
+        *reinterpret_cast<uint4*>(my + b * 1024) = make_uint4(w0 & 255u, 0u, w0 >> 8, 0u);
+        *reinterpret_cast<uint4*>(my + b * 1024 + 512) = make_uint4(w1 & 255u, 0u, w1 >> 8, 0u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
-                         :: "l"(dst + g0), "r"(sbuf + (uint32_t)boff), "r"(cnt * 8) : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 1024;\n\tcp.async.bulk.commit_group;"
+                         :: "l"(dst), "r"(sbuf + (uint32_t)b * 1024u) : "memory");
+            bulk_wait_read(nb - 1);
         }
+        __syncwarp();
+        src += 64; dst += 128;
+        b = b + 1 == nb ? 0 : b + 1;
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (tail) {
+        if (2 * lane < tail) {
+            const uint32_t w0 = src[0];
+            *reinterpret_cast<uint4*>(my + b * 1024) = make_uint4(w0 & 255u, 0u, w0 >> 8, 0u);
+        }
+        if (2 * (lane + 32) < tail) {
+            const uint32_t w1 = src[32];
+            *reinterpret_cast<uint4*>(my + b * 1024 + 512) = make_uint4(w1 & 255u, 0u, w1 >> 8, 0u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
+                         :: "l"(dst), "r"(sbuf + (uint32_t)b * 1024u), "r"(tail * 8) : "memory");
+    }
+    if (lane == 0) bulk_wait_read(0);                            // the buffers are shared memory of a CTA about to exit
     __syncwarp();
 }
 
@@ -104,11 +124,17 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
         AL = s2;
     }
     const int n_deep = L - 2;                                    // ancestors kept in shared memory: depths 0 .. L-3
-    // [warp][n_deep][H][TPT][32]: a warp's accumulators are one contiguous span, reused as the staging buffers of the
-    // bulk-store flush once the last climb is done
-    const int acc_warp = n_deep * H * TPT * 32;                  // f2 elements per warp
-    f2* ACC = reinterpret_cast<f2*>(smem + off) + (size_t)warp * acc_warp + lane;
-    if (BP) off += (size_t)n_deep * H * TPT * NT * sizeof(f2);
+    // Parked accumulators.  Memoised variants: [warp][n_deep][H][TPT][32], a warp's accumulators are one contiguous span
+    // (host: padded to whole 1 KB buffers) that doubles as the ring of the bulk-store flush once the last climb is done.
+    // The others keep [n_deep][H][TPT][NT] carved from n_deep: with the per-warp form (or merely a carve that depends on a
+    // kernel argument) ptxas moved one of their two hot matvecs from LDCU.64 / uniform registers to LDC.64 and the
+    // given-leaves BP lost 12 % (0.115 -> 0.128 ms; SASS: 213 -> 113 LDCU.64).
+    constexpr int AST = MEMO ? 32 : NT;                          // stride between the (i, t) rows of one level
+    const int acc_warp = MEMO ? a.acc_stride : 0;                // f2 elements per warp
+    f2* ACC = reinterpret_cast<f2*>(smem + off);                 // (+ acc_tid at the use sites, AFTER the uniform offsets:
+    const int acc_tid = MEMO ? warp * acc_warp + lane : tid;     //  the order decides LDCU vs LDC as well)
+    if constexpr (MEMO) off += (size_t)acc_warp * T2_WARPS * sizeof(f2);
+    else if (BP) off += (size_t)n_deep * H * TPT * NT * sizeof(f2);
     const int n_rng = n_deep + (SPARE ? 0 : 1);                  // levels 1 .. L-2 (+ L-1 when it has no spare word)
     uint32_t* RNG = reinterpret_cast<uint32_t*>(smem + off);     // [n_rng][3][TPT][NT]  words 1..3 of the cached Philox blocks
     if (PHILOX) off += (size_t)n_rng * 3 * TPT * NT * 4;
@@ -266,14 +292,14 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
 #pragma unroll
             for (int t = 0; t < TPT; ++t)
 #pragma unroll
-                for (int i = 0; i < H; ++i) u[t][i] = f2_mul(u[t][i], A ? A[(i * TPT + t) * 32] : accT[t][i]);
+                for (int i = 0; i < H; ++i) u[t][i] = f2_mul(u[t][i], A ? A[(i * TPT + t) * AST] : accT[t][i]);
         }
         if (!last) {
 #pragma unroll
             for (int t = 0; t < TPT; ++t)
 #pragma unroll
                 for (int i = 0; i < H; ++i) {
-                    if (A) A[(i * TPT + t) * 32] = u[t][i]; else accT[t][i] = u[t][i];
+                    if (A) A[(i * TPT + t) * AST] = u[t][i]; else accT[t][i] = u[t][i];
                 }
             return false;
         }
@@ -290,15 +316,24 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
     auto climb = [&](int j, int cj, int c1, const f2 (&h)[TPT][H]) {
         bool up;
         if constexpr (MEMO) {                                    // h IS the message to the parent: fold it into the parked product
-            up = cj == S - 1;
+            up = cj == S - 1;                                    // (uniform branches: selects cost 2 S q issue slots per node)
+            if (cj == 0) {
 #pragma unroll
-            for (int t = 0; t < TPT; ++t) {
+                for (int t = 0; t < TPT; ++t)
 #pragma unroll
-                for (int i = 0; i < H; ++i) {
-                    const f2 u = cj != 0 ? f2_mul(h[t][i], accT[t][i]) : h[t][i];
-                    if (up) msg[t][i] = u; else accT[t][i] = u;
+                    for (int i = 0; i < H; ++i) accT[t][i] = h[t][i];
+            } else if (!up) {
+#pragma unroll
+                for (int t = 0; t < TPT; ++t)
+#pragma unroll
+                    for (int i = 0; i < H; ++i) accT[t][i] = f2_mul(h[t][i], accT[t][i]);
+            } else {
+#pragma unroll
+                for (int t = 0; t < TPT; ++t) {
+#pragma unroll
+                    for (int i = 0; i < H; ++i) msg[t][i] = f2_mul(h[t][i], accT[t][i]);
+                    f2_normalize<Q>(msg[t]);
                 }
-                if (up) f2_normalize<Q>(msg[t]);
             }
         } else {
 #pragma unroll
@@ -311,14 +346,14 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
             // nothing but the constant-bank address, so they stay in UNIFORM registers (LDCU.64 + FFMA2 with a UR operand)
             up = climb_step(tab.v + (base0 + cj) * (Q * QS), cj != 0, cj == S - 1, nullptr);
         }
-        if (up) up = climb_step(tab.v + (base1 + c1) * (Q * QS), c1 != 0, c1 == S - 1, ACC + (size_t)(L - 3) * H * TPT * 32);
+        if (up) up = climb_step(tab.v + (base1 + c1) * (Q * QS), c1 != 0, c1 == S - 1, ACC + (size_t)(L - 3) * H * TPT * AST + acc_tid);
         if (up && L >= 4) {
-            f2* A = ACC + (size_t)(L - 4) * H * TPT * 32;
+            f2* A = ACC + (size_t)(L - 4) * H * TPT * AST + acc_tid;
             for (int l = L - 3; l > 0; --l) {
                 const int idx = ghm_div_pow(j, L - 1 - l, d);    // index of the path node at depth l
                 const int c = idx - (idx / S) * S;
                 if (!climb_step(tab.v + ((l - 1) * S + c) * (Q * QS), c != 0, c == S - 1, A)) break;
-                A -= H * TPT * 32;
+                A -= H * TPT * AST;
             }
         }
     };
@@ -339,48 +374,59 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
     int cj = 0, c1 = 0;                                          // j mod s, (j / s) mod s
     // One straight-line block: Philox of node j+2 (-> rbN), draws + leaf rows of node j+1 (rbU -> hL), BP climb of node j (hU).
     // (measured: guarding the sampling half with `jn < n1` instead of peeling the last climb costs 4 %)
-    auto body = [&](int j, uint4 (&rbU)[TPT], uint4 (&rbN)[TPT], f2 (&hU)[TPT][H], f2 (&hL)[TPT][H]) {
-        const int jn = j + 1;
-        const int cjn = cj + 1 == S ? 0 : cj + 1;
-        if (PHILOX && cjn == 0) redraw_ancestors(jn);
-        if (PHILOX) {
+    if constexpr (MEMO) {                                        // unrolled by two: the buffers swap roles, no register copies
+        auto body = [&](int j, int cjn, uint4 (&rbU)[TPT], uint4 (&rbN)[TPT], f2 (&hU)[TPT][H], f2 (&hL)[TPT][H]) {
+            const int jn = j + 1;
+            if (cjn == 0) redraw_ancestors(jn);
 #pragma unroll
             for (int t = 0; t < TPT; ++t)                        // (one block past the end is computed and dropped)
                 rbN[t] = ghm_rng_block(a.seed, tree[t], (uint32_t)L, (uint32_t)(jn + 1), GHM_STREAM_TREE);
-        }
-        if constexpr (MEMO) {
             // consume the prefetched row BEFORE the next gathers are issued: a wait placed behind them shares their
             // scoreboard and sits out a full L2 round trip (ncu r02x: 29 % of the stall samples on the first use)
             climb(j, cj, c1, hU);
             sample_node(jn, cjn, rbU, hL);
-        } else {
-            sample_node(jn, cjn, rbU, hL);
-            if (BP) climb(j, cj, c1, hU);
-        }
-        cj = cjn;
-        if (cjn == 0) c1 = c1 + 1 == S ? 0 : c1 + 1;
-    };
-    if constexpr (MEMO) {                                        // unrolled by two: the buffers swap roles, no register copies
+        };
+        auto advance = [&](int cjn) {
+            cj = cjn;
+            if (cjn == 0) c1 = c1 + 1 == S ? 0 : c1 + 1;
+        };
         int j = 0;
         for (; j + 2 <= n1 - 1; j += 2) {
-            body(j, rbA, rbB, hcur, hnext);
-            body(j + 1, rbB, rbA, hnext, hcur);
+            int cjn = cj + 1 == S ? 0 : cj + 1;
+            body(j, cjn, rbA, rbB, hcur, hnext);
+            advance(cjn);
+            cjn = cj + 1 == S ? 0 : cj + 1;
+            body(j + 1, cjn, rbB, rbA, hnext, hcur);
+            advance(cjn);
         }
         if constexpr (S % 2 == 0) {                              // n1 = s^(L-1) even: one node pair is left (odd s: none)
-            body(j, rbA, rbB, hcur, hnext);
+            const int cjn = cj + 1 == S ? 0 : cj + 1;
+            body(j, cjn, rbA, rbB, hcur, hnext);
+            advance(cjn);
             climb(n1 - 1, cj, c1, hnext);
         } else {
             climb(n1 - 1, cj, c1, hcur);
         }
     } else {
         for (int j = 0; j < n1 - 1; ++j) {
-            body(j, rbA, rbB, hcur, hnext);
+            const int jn = j + 1;
+            const int cjn = cj + 1 == S ? 0 : cj + 1;
+            if (PHILOX && cjn == 0) redraw_ancestors(jn);
+            if (PHILOX) {
+#pragma unroll
+                for (int t = 0; t < TPT; ++t)                    // (one block past the end is computed and dropped)
+                    rbB[t] = ghm_rng_block(a.seed, tree[t], (uint32_t)L, (uint32_t)(jn + 1), GHM_STREAM_TREE);
+            }
+            sample_node(jn, cjn, rbA, hnext);
+            if (BP) climb(j, cj, c1, hcur);
 #pragma unroll
             for (int t = 0; t < TPT; ++t) {
                 rbA[t] = rbB[t];
 #pragma unroll
                 for (int i = 0; i < H; ++i) hcur[t][i] = hnext[t][i];
             }
+            cj = cjn;
+            if (cjn == 0) c1 = c1 + 1 == S ? 0 : c1 + 1;
         }
         if (BP) climb(n1 - 1, cj, c1, hcur);
     }
@@ -391,9 +437,9 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
         // filled buffer to cp.async.bulk.  The STG.128 loop it replaces ran one store at a time -- the next store's data
         // registers were the previous store's, and each wait was a round trip of the busy LSU queue (ncu r02y: 28 % of
         // the kernel's stall samples) -- and every CTA of a wave reached it at the same moment.
-        if (BP && a.leaf_dtype == GHM_LEAF_I64 && warp_tree0 + WTREES <= a.B && acc_warp * (int)sizeof(f2) >= 1024)
+        if (MEMO && a.leaf_dtype == GHM_LEAF_I64 && warp_tree0 + WTREES <= a.B && acc_warp * (int)sizeof(f2) >= 1024)
             stage_flush_bulk_i64(stage, WTREES * nL, reinterpret_cast<int64_t*>(a.leaves) + warp_tree0 * nL,
-                                 reinterpret_cast<unsigned char*>(ACC - lane), acc_warp * (int)sizeof(f2), lane);
+                                 reinterpret_cast<unsigned char*>(ACC + warp * acc_warp), min(acc_warp * (int)sizeof(f2) / 1024, 4), lane);
         else
             stage_flush_flat(stage, WTREES, a.leaves, a.leaf_dtype, warp_tree0, a.B, nL, lane);
     }
@@ -434,7 +480,10 @@ static int launch_tree_fast(const ghm_model* m, const TreeArgs& a0, cudaStream_t
     if (MEMO && !d.leaf_memo) return ghm_fail(GHM_EUNSUP, "internal: leaf memo missing (L=%d s=%d q=%d)", d.L, d.s, d.q);
     if (BP && !MEMO) dyn += ((size_t)S * Q * ((Q % 4 == 2 && MODE == MODE_GIVEN) ? Q : QS) * 4 + 15) / 16 * 16;
     if (MODE == MODE_PHILOX) dyn += ((size_t)d.n_mat * d.q * d.q * 4 + 15) / 16 * 16;
-    if (BP) dyn += (size_t)n_deep * (Q / 2) * TPT * T2_NT * sizeof(float2);
+    a.acc_stride = n_deep * (Q / 2) * TPT * 32;                   // f2 per warp; memoised int64 sampling: whole 1 KB flush buffers (<= 4)
+    if (MEMO && a.leaves && a.leaf_dtype == GHM_LEAF_I64 && a.acc_stride * 8 < 4096)
+        a.acc_stride = (a.acc_stride * 8 + 1023) / 1024 * 128;
+    if (BP) dyn += (size_t)a.acc_stride * T2_WARPS * sizeof(float2);
     if (MODE == MODE_PHILOX) {
         const int n_rng = n_deep + ((S & 3) != 0 ? 0 : 1);
         dyn += (size_t)n_rng * 3 * TPT * T2_NT * 4 + ((size_t)n_deep * TPT * T2_NT + 15) / 16 * 16;

@@ -63,6 +63,7 @@ struct TreeArgs {
     int stage_stride;      // bytes per staged tree row
     int stage_bytes;       // bytes of staging per warp
     int base0, base1;      // index of the matrices into depth L-1 / L-2 (child 0): (L-2)*s, (L-3)*s
+    int acc_stride;        // k_tree_fast: f2 elements of shared memory per warp for the parked accumulators / flush ring
 };
 
 // ------------------------------------------------------------------------------------------------
