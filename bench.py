@@ -56,15 +56,19 @@ METRIC = "JGHM trees/sec (sample + full BP posterior)"
 N_SM = 148
 # Figures of the dominant kernel taken from its committed `ncu --set full` capture (per launch of 327 680 trees)
 KTREE = {
-    "kernel": "k_tree_fast<Q=10,S=3,PHILOX,BP> (fused sampler + root-posterior BP, two trees per thread, int64 leaves out)",
+    "kernel": "k_tree_fast<Q=10,S=3,PHILOX,BP> (fused sampler + root-posterior BP: leaf memo, one tree per thread at 7 CTAs/SM, "
+              "int64 leaves out through cp.async.bulk)",
     "source": "profiles/r02_ncu_full_k_tree_fast.csv",
-    "dram_bytes_per_tree": 518.8,          # 169.92 MB written + 0.09 MB read per launch (below the 696 B/tree algorithmic
+    "dram_bytes_per_tree": 518.4,          # 169.62 MB written + 0.23 MB read per launch (below the 696 B/tree algorithmic
                                            # figure: the tail of the leaves is still in the 126 MB L2 when the kernel ends)
-    "warp_inst_per_tree": 106626560 / 327680,
-    "share": 0.96,                         # of the GPU time in the serialised ncu launch list of this script (profiles/r02_launches_bench_clip.csv)
-    "note": "no single unit is the wall: issue slots 0.60, FMA-heavy pipe 0.54 (FFMA2 2.1 clk, Philox IMAD.WIDE 4.3 clk per warp "
-            "instruction), ALU pipe 0.35, shared-memory pipe 0.52 at 4 warps per scheduler (123 registers, 54 KB); a fifth CTA "
-            "per SM measured 7 % SLOWER; the HBM fraction is reported, not padded; see roofline.secondary and DESIGN.md 3.1",
+    "warp_inst_per_tree": 97016320 / 327680,
+    "share": 0.95,                         # of the GPU time in the serialised ncu launch list of this script (profiles/r02_launches_bench_clip.csv)
+    "note": "issue slots 0.71 at 7 warps per scheduler (70 registers, 30.8 KB), ALU pipe 0.39, FMA-heavy pipe 0.33 (Philox "
+            "IMAD.WIDE 4.3 clk per warp instruction), uniform datapath 0.22, L1 0.77; 31 % of the stall samples sit in the "
+            "int64 flush at the end of a tile (bulk copies draining at HBM write speed while every warp of the wave flushes), "
+            "10 % in the dependent chain of the last climb; the leaf memo removed 27 of the 40 matvecs of a tree (107 -> 97 M "
+            "warp instructions per launch at twice the warps); the HBM fraction is reported, not padded; see roofline.secondary "
+            "and DESIGN.md 3.1",
 }
 
 

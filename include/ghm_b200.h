@@ -79,7 +79,9 @@ GHM_API int ghm_model_destroy(ghm_model_t* m);
 /* New tables for an existing model of the same (L, s, q, ti): what constructing a new sampler per p_flip does in
  * the reference's sweeps (figures/eval-clip-ood.py:76-79, eval-cdm-ood.py:104-109, eval-vlm-ood.py:104-109).
  * Tables are derived on the host and uploaded with ONE async copy from pinned memory on `stream`
- * (ghm_model_table_bytes() bytes); kernels enqueued on `stream` afterwards use them. */
+ * (ghm_model_table_bytes() bytes), followed on the same stream by one small kernel that tabulates the message of a
+ * depth-(L-1) node as a function of its s leaf states (:191-208; the leaf memo of the fused sampler + BP_CLS kernel);
+ * kernels enqueued on `stream` afterwards use them. */
 GHM_API int ghm_model_update(ghm_model_t* m, const double* T_host, const double* p_y_host, void* stream);
 GHM_API int64_t ghm_model_table_bytes(const ghm_model_t* m);
 /* wide-q models only (ignored for q <= 16): pick the GEMM arithmetic, see GHM_GEMM_* */

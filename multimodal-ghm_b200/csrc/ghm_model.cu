@@ -87,9 +87,11 @@ static int validate_tables(const GhmDev& d, const double* T_host, const double* 
 }
 
 // fills the host slab from the caller's float64 matrices (validated by validate_tables)
-static int derive_tables(const GhmDev& d, const double* T_host, const double* p_y_host, char* hs) {
-    int vrc = validate_tables(d, T_host, p_y_host);
-    if (vrc) return vrc;
+static int derive_tables(const GhmDev& d, const double* T_host, const double* p_y_host, char* hs, bool validated = false) {
+    if (!validated) {
+        int vrc = validate_tables(d, T_host, p_y_host);
+        if (vrc) return vrc;
+    }
     const SlabLayout o = slab_layout(d);
     const int q = d.q, QP = d.QP, QS = d.QS;
     const size_t nm = (size_t)d.n_mat, QQ = (size_t)QP * QP;
@@ -285,7 +287,7 @@ extern "C" int ghm_model_update(ghm_model_t* m, const double* T_host, const doub
         GHM_CUDA_TRY(cudaEventCreateWithFlags(&m->upload_evs[next], cudaEventDisableTiming));
     }
     GHM_CUDA_TRY(cudaEventSynchronize(m->upload_evs[next]));     // the upload that last used this pinned buffer has consumed it
-    int rc = derive_tables(m->d, T_host, p_y_host, (char*)m->h_slabs[next]);
+    int rc = derive_tables(m->d, T_host, p_y_host, (char*)m->h_slabs[next], true);
     if (rc) return rc;
     GHM_CUDA_TRY(cudaMemcpyAsync(m->slabs[next], m->h_slabs[next], o.status, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     point_tables(m, next);

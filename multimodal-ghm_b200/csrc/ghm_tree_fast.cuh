@@ -14,12 +14,15 @@
 //     the leaf-row product of the next node is in registers before the climb that needs it starts;
 //   * no odometer: child digits of the rarely taken deep steps come from `j / s^k` by the host's multiply-high
 //     magics (uniform datapath), the two hot steps use running counters;
-//   * LEAF MEMO (where ghm_memo_ok(Q, S): the table stays <= 1 MB): the message of a depth-(L-1) node to its parent is a
-//     function of (child number, s leaf states) only, tabulated per table upload (GhmDev::leaf_memo, built on the device
-//     by k_build_leaf_memo with the same operations).  The node then costs ONE gathered row (L2 / L1 resident, fetched a
-//     full iteration ahead into the other half of a register ping-pong) instead of s shared-memory row gathers, the
-//     row product, a rescale and a q x q matvec: 27 of the 40 matvecs of an L = 4, s = 3 tree disappear.  The loop is
-//     unrolled by two so the prefetched row and the Philox block change roles without register copies.
+//   * LEAF MEMO (sampling + BP, where ghm_memo_ok(Q, S): the table stays <= 1 MB): the message of a depth-(L-1) node to
+//     its parent is a function of (child number, s leaf states) only, tabulated per table upload (GhmDev::leaf_memo, built
+//     on the device by k_build_leaf_memo with the same operations, so the posteriors are bit-identical).  The node then
+//     costs ONE gathered row (L1 / L2 resident, fetched a full iteration ahead into the other half of a register
+//     ping-pong, loop unrolled by two) instead of s shared-memory row gathers, the row product, a rescale and a q x q
+//     matvec: 27 of the 40 matvecs of an L = 4, s = 3 tree disappear.  These variants run ONE tree per thread at 7 (q <= 10)
+//     or 6 CTAs per SM (FastCfg) and flush int64 leaves through cp.async.bulk from a ring of 1 KB buffers carved from the
+//     warp's accumulator span.  Given-leaves BP keeps the row products (no Philox work to hide the gathers behind).
+//     Measurements and what was tried on the way: DESIGN.md 3.1, round 2b.
 #pragma once
 
 // Flush of one warp's staged leaf bytes st[0 .. n) (n a multiple of 32) as n contiguous int64 at dst (16-byte aligned)

@@ -188,7 +188,9 @@ def test_leaf_dtype_alignment_and_tpt_variants_agree(ops, L, s, q):
     assert torch.equal(u8["leaves"].long(), ref["leaves"]) and torch.equal(u8["post"], ref["post"])
     nol = m.sample(B, seed=5, root_mode=ops.ROOT_UNIFORM, want_leaves=False, want_post=True)
     assert torch.equal(nol["post"], ref["post"]) and torch.equal(nol["root"], ref["root"])
-    # unaligned int64 / uint8 destinations: a view that starts 8 (resp. 1) bytes into an allocation
+    # unaligned int64 / uint8 destinations: a view that starts 8 (resp. 1) bytes into an allocation.  These launches take the
+    # generic one-tree-per-thread kernel (per-node row products + matvec), `ref` the memoised fast variant: torch.equal on
+    # the posteriors is the bit-identity check of the leaf memo (ghm_common.cuh: GhmDev::leaf_memo)
     for dt in (torch.int64, torch.uint8):
         buf = torch.zeros(B * nL + 1, dtype=dt, device="cuda:0")
         view = buf[1:].view(B, nL)
