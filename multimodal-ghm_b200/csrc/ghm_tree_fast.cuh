@@ -84,6 +84,7 @@ __device__ __forceinline__ void stage_flush_bulk_i64(const uint8_t* st, int n, i
 template <int Q, int S, int MODE, bool BP>
 struct FastCfg {
     static constexpr bool MEMO = BP && MODE == MODE_PHILOX && ghm_memo_ok(Q, S);
+    static constexpr bool RING = !BP && MODE == MODE_PHILOX;      // sampling only: same form, the "accumulator span" is just the flush ring
     static constexpr int TPT = MEMO ? 1 : 2;
     static constexpr int CTAS = MEMO ? (Q <= 10 ? 7 : 6) : 4;
 };
@@ -95,7 +96,7 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
     constexpr int TPT = FastCfg<Q, S, MODE, BP>::TPT, NT = T2_NT, H = Q / 2, QS = (Q + 3) / 4 * 4, WTREES = 32 * TPT;
     constexpr bool SPARE = (S & 3) != 0;                         // node j is drawn from the spare word of its leaf block
     constexpr bool PHILOX = MODE == MODE_PHILOX;
-    constexpr bool MEMO = FastCfg<Q, S, MODE, BP>::MEMO;
+    constexpr bool MEMO = FastCfg<Q, S, MODE, BP>::MEMO, RING = FastCfg<Q, S, MODE, BP>::RING;
     // Shared-memory stride of the gathered leaf rows T_c^T[x, :].  Each lane reads the row of ITS leaf state, so the
     // loads are true gathers: with 48-byte rows read as LDS.128 + LDS.128 + LDS.64 the ten rows of q = 10 fall on eight
     // 16-byte bank groups (rows 0/8 and 1/9 collide: 0.5 extra wavefronts per load, ncu r02k); with 40-byte rows read
@@ -133,10 +134,10 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
     // kernel argument) ptxas moved one of their two hot matvecs from LDCU.64 / uniform registers to LDC.64 and the
     // given-leaves BP lost 12 % (0.115 -> 0.128 ms; SASS: 213 -> 113 LDCU.64).
     constexpr int AST = MEMO ? 32 : NT;                          // stride between the (i, t) rows of one level
-    const int acc_warp = MEMO ? a.acc_stride : 0;                // f2 elements per warp
+    const int acc_warp = (MEMO || RING) ? a.acc_stride : 0;      // f2 elements per warp
     f2* ACC = reinterpret_cast<f2*>(smem + off);                 // (+ acc_tid at the use sites, AFTER the uniform offsets:
     const int acc_tid = MEMO ? warp * acc_warp + lane : tid;     //  the order decides LDCU vs LDC as well)
-    if constexpr (MEMO) off += (size_t)acc_warp * T2_WARPS * sizeof(f2);
+    if constexpr (MEMO || RING) off += (size_t)acc_warp * T2_WARPS * sizeof(f2);
     else if (BP) off += (size_t)n_deep * H * TPT * NT * sizeof(f2);
     const int n_rng = n_deep + (SPARE ? 0 : 1);                  // levels 1 .. L-2 (+ L-1 when it has no spare word)
     uint32_t* RNG = reinterpret_cast<uint32_t*>(smem + off);     // [n_rng][3][TPT][NT]  words 1..3 of the cached Philox blocks
@@ -440,7 +441,7 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
         // filled buffer to cp.async.bulk.  The STG.128 loop it replaces ran one store at a time -- the next store's data
         // registers were the previous store's, and each wait was a round trip of the busy LSU queue (ncu r02y: 28 % of
         // the kernel's stall samples) -- and every CTA of a wave reached it at the same moment.
-        if (MEMO && a.leaf_dtype == GHM_LEAF_I64 && warp_tree0 + WTREES <= a.B && acc_warp * (int)sizeof(f2) >= 1024)
+        if ((MEMO || RING) && a.leaf_dtype == GHM_LEAF_I64 && warp_tree0 + WTREES <= a.B && acc_warp * (int)sizeof(f2) >= 1024)
             stage_flush_bulk_i64(stage, WTREES * nL, reinterpret_cast<int64_t*>(a.leaves) + warp_tree0 * nL,
                                  reinterpret_cast<unsigned char*>(ACC + warp * acc_warp), min(acc_warp * (int)sizeof(f2) / 1024, 4), lane);
         else
@@ -483,10 +484,12 @@ static int launch_tree_fast(const ghm_model* m, const TreeArgs& a0, cudaStream_t
     if (MEMO && !d.leaf_memo) return ghm_fail(GHM_EUNSUP, "internal: leaf memo missing (L=%d s=%d q=%d)", d.L, d.s, d.q);
     if (BP && !MEMO) dyn += ((size_t)S * Q * ((Q % 4 == 2 && MODE == MODE_GIVEN) ? Q : QS) * 4 + 15) / 16 * 16;
     if (MODE == MODE_PHILOX) dyn += ((size_t)d.n_mat * d.q * d.q * 4 + 15) / 16 * 16;
-    a.acc_stride = n_deep * (Q / 2) * TPT * 32;                   // f2 per warp; memoised int64 sampling: whole 1 KB flush buffers (<= 4)
+    constexpr bool RING = FastCfg<Q, S, MODE, BP>::RING;
+    a.acc_stride = BP ? n_deep * (Q / 2) * TPT * 32 : 0;          // f2 per warp; memoised int64 sampling: whole 1 KB flush buffers (<= 4)
     if (MEMO && a.leaves && a.leaf_dtype == GHM_LEAF_I64 && a.acc_stride * 8 < 4096)
         a.acc_stride = (a.acc_stride * 8 + 1023) / 1024 * 128;
-    if (BP) dyn += (size_t)a.acc_stride * T2_WARPS * sizeof(float2);
+    if (RING && a.leaves && a.leaf_dtype == GHM_LEAF_I64) a.acc_stride = 3 * 128;   // sampling only: a ring of three buffers
+    if (BP || RING) dyn += (size_t)a.acc_stride * T2_WARPS * sizeof(float2);
     if (MODE == MODE_PHILOX) {
         const int n_rng = n_deep + ((S & 3) != 0 ? 0 : 1);
         dyn += (size_t)n_rng * 3 * TPT * T2_NT * 4 + ((size_t)n_deep * TPT * T2_NT + 15) / 16 * 16;
