@@ -61,26 +61,43 @@ __global__ void __launch_bounds__(PAR_NT) k_sample_parity(const GhmDev d, const 
 // ------------------------------------------------------------------------------------------------
 template <int Q>
 __global__ void __launch_bounds__(128) k_build_leaf_memo(const GhmDev d, float* __restrict__ out, int rows) {
+    // one thread per (row, state pair): the rescaled leaf-row product is recomputed by the Q/2 threads of a row (cheap),
+    // each then forms its own pair of the matvec -- independent loads, two dependent global round trips in all
     constexpr int H = Q / 2, QS = (Q + 3) / 4 * 4;
-    const int r = blockIdx.x * 128 + threadIdx.x;
+    const int idx = blockIdx.x * 128 + threadIdx.x;
+    const int r = idx / H, i = idx - r * H;
     if (r >= rows) return;
     const int q = d.q, s = d.s, L = d.L;
-    int x[4], rem = r;
-    for (int c = s - 1; c >= 0; --c) { x[c] = rem % q; rem /= q; }   // row = ((cj*q + x_0)*q + x_1)*q + ...
+    int xs[4] = {0, 0, 0, 0}, rem = r;                           // row = ((cj*q + x_0)*q + x_1)*q + ...
+#pragma unroll
+    for (int c = 3; c >= 0; --c)
+        if (c < s) { xs[c] = rem % q; rem /= q; }
     const int cj = rem;
     f2 h[H];
-    for (int c = 0; c < s; ++c) {
-        f2 row[H];
-        f2_load_row<Q>(d.TTp + ((size_t)(d.mat_off[L] + c) * Q + x[c]) * QS, row);
 #pragma unroll
-        for (int i = 0; i < H; ++i) h[i] = c == 0 ? row[i] : f2_mul(h[i], row[i]);
+    for (int c = 0; c < 4; ++c) {
+        if (c < s) {
+            f2 row[H];
+            f2_load_row<Q>(d.TTp + ((size_t)(d.mat_off[L] + c) * Q + xs[c]) * QS, row);
+#pragma unroll
+            for (int k = 0; k < H; ++k) h[k] = c == 0 ? row[k] : f2_mul(h[k], row[k]);
+        }
     }
     f2_normalize<Q>(h);
-    f2 u[H];
-    f2_matvec_up1<Q, QS>(d.TTp + (size_t)(d.mat_off[L - 1] + cj) * Q * QS, h, u);
-    float* o = out + (size_t)r * QS;
+    const float* TT = d.TTp + (size_t)(d.mat_off[L - 1] + cj) * Q * QS + 2 * i;
+    f2 u = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < QS; ++k) o[k] = k < Q ? f2_elem<Q>(u, k) : 0.f;
+    for (int b = 0; b < Q; ++b) {                                // the pair-i column of f2_matvec_up1, same operation order
+        const f2 t = *reinterpret_cast<const f2*>(TT + b * QS);
+        const float xb = f2_elem<Q>(h, b);
+        u = b == 0 ? f2_muls(t, xb) : f2_fmas(t, xb, u);
+    }
+    float* o = out + (size_t)r * QS;
+    *reinterpret_cast<f2*>(o + 2 * i) = u;
+    if (i == 0) {
+#pragma unroll
+        for (int k = Q; k < QS; ++k) o[k] = 0.f;
+    }
 }
 
 int ghm_build_leaf_memo(const ghm_model* m, cudaStream_t st) {
@@ -88,7 +105,7 @@ int ghm_build_leaf_memo(const ghm_model* m, cudaStream_t st) {
     const size_t rows = ghm_leaf_memo_rows(d);
     if (!rows || !d.leaf_memo) return GHM_OK;
     float* out = const_cast<float*>(d.leaf_memo);
-    const unsigned grid = (unsigned)((rows + 127) / 128);
+    const unsigned grid = (unsigned)((rows * (size_t)(d.QP / 2) + 127) / 128);
     switch (d.QP) {
         case 4: k_build_leaf_memo<4><<<grid, 128, 0, st>>>(d, out, (int)rows); break;
         case 8: k_build_leaf_memo<8><<<grid, 128, 0, st>>>(d, out, (int)rows); break;
