@@ -80,7 +80,7 @@ __device__ __forceinline__ void stage_flush_bulk_i64(const uint8_t* st, int n, i
 // scheduler, issue 0.48, every pipe under 0.36), and what two trees per thread used to share -- the constant-bank table
 // loads of the leaf-level matvec -- is gone: ONE tree per thread in 70-80 registers and half the shared memory puts 7
 // (q <= 10) or 6 CTAs on an SM instead of 4 (measured, L4 s3 q10: 0.1524 -> 0.1390 ms).  Without the memo the two-tree
-// form stays (one tree per thread measured equal there).
+// form stays (one tree per thread measured equal there, and 20 % slower for sampling only: DESIGN.md).
 template <int Q, int S, int MODE, bool BP>
 struct FastCfg {
     static constexpr bool MEMO = BP && MODE == MODE_PHILOX && ghm_memo_ok(Q, S);
@@ -436,9 +436,9 @@ k_tree_fast(const __grid_constant__ GhmDev d, const __grid_constant__ TreeArgs a
     }
 
     if (PHILOX && use_stage) {
-        // int64 leaves of a full tile leave through the bulk-copy engine: the warp expands its staged bytes into two
-        // alternating buffers (its accumulator span, dead by now) with conflict-free STS.128 and one lane hands each
-        // filled buffer to cp.async.bulk.  The STG.128 loop it replaces ran one store at a time -- the next store's data
+        // int64 leaves of a full tile leave through the bulk-copy engine: the warp expands its staged bytes into a ring of
+        // 1 KB buffers (memoised variants: its accumulator span, dead by now; sampling only: 3 KB carved for the purpose)
+        // with conflict-free STS.128 and one lane hands each filled buffer to cp.async.bulk.  The STG.128 loop it replaces ran one store at a time -- the next store's data
         // registers were the previous store's, and each wait was a round trip of the busy LSU queue (ncu r02y: 28 % of
         // the kernel's stall samples) -- and every CTA of a wave reached it at the same moment.
         if ((MEMO || RING) && a.leaf_dtype == GHM_LEAF_I64 && warp_tree0 + WTREES <= a.B && acc_warp * (int)sizeof(f2) >= 1024)
