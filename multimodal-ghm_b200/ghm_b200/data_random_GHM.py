@@ -497,9 +497,12 @@ class _SamplerBase:
         buffering): the current stream waits for every lazy evaluation that read version v-1 or older (normally long
         complete), then the version counter advances."""
         v = getattr(self, "_table_version", 0)
+        cur = None                                               # (looked up once: torch.cuda.current_stream costs ~9 us a call)
         for ev, ver in getattr(self, "_lazy_events", ()):
             if ver <= v - 1:
-                torch.cuda.current_stream(self.device).wait_event(ev)
+                if cur is None:
+                    cur = torch.cuda.current_stream(self.device)
+                cur.wait_event(ev)
         self._table_version = v + 1
 
     def _side_stream(self):
